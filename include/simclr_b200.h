@@ -1,0 +1,226 @@
+/*
+ * simclr_b200 -- C-ABI of the B200-native SimCLR pretrain step.
+ *
+ * The reference (google-research/simclr) has no FFI layer: its hot path is
+ * Python calling TensorFlow ops.  This header is therefore the *new* boundary
+ * a maintainer binds with ctypes; every entry point cites
+ * the reference call site whose arithmetic it replaces (paths relative to the
+ * reference repository root).
+ *
+ * Conventions:
+ *   - plain C, no torch types; all tensor pointers are DEVICE pointers owned by
+ *     the caller; the library never allocates or frees device memory and keeps
+ *     no reference after return.
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as
+ *     void*); no hidden synchronisation, no default-stream use => capturable in
+ *     a CUDA graph.
+ *   - return value: 0 on success, negative simclr_status for argument errors
+ *     (checked before launch), positive = cudaError_t.  simclr_last_error()
+ *     returns thread-local text for the last failure.
+ *   - activations are NHWC, conv kernels HWIO, dense kernels [in,out], exactly
+ *     the layouts of the reference's variables (tf2/resnet.py:196-208,
+ *     tf2/model.py:143-147).  `dtype` selects the activation storage type.
+ */
+#ifndef SIMCLR_B200_H_
+#define SIMCLR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMCLR_API __attribute__((visibility("default")))
+
+enum simclr_status {
+  SIMCLR_OK = 0,
+  SIMCLR_ERR_INVALID_ARG = -1,
+  SIMCLR_ERR_UNSUPPORTED = -2,
+  SIMCLR_ERR_WORKSPACE = -3,
+  SIMCLR_ERR_DRIVER = -4
+};
+
+enum simclr_dtype { SIMCLR_F32 = 0, SIMCLR_BF16 = 1 };
+
+SIMCLR_API int simclr_version(void);
+SIMCLR_API const char* simclr_last_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * NT-Xent objective  (tf2/objective.py:35-89)
+ * ------------------------------------------------------------------------- */
+
+/* l2-normalise rows (tf2/objective.py:53-54; tf.math.l2_normalize eps 1e-12).
+ * hidden [rows,dim] -> z [rows,dim], inv_norm [rows].  hidden_norm==0 copies. */
+SIMCLR_API int simclr_ntxent_normalize(const float* hidden, int64_t rows, int64_t dim, int hidden_norm,
+                                       float* z, float* inv_norm, void* stream);
+
+SIMCLR_API size_t simclr_ntxent_workspace_bytes(int64_t B, int64_t R, int64_t D);
+
+/* Forward for the local 2B rows against all 2*R*B gathered rows.
+ * z_all is the all-gather of every replica's z, layout [R][2][B][D]
+ * (replaces tpu_cross_replica_concat, tf2/objective.py:92-127; R==1: local z).
+ * Outputs: logits_ab [B][R*B] (tf2/objective.py:80, nullable), lse [2][B],
+ * row_loss [2][B], loss [1] = mean_i(loss_a_i + loss_b_i) (tf2/objective.py:83-87). */
+SIMCLR_API int simclr_ntxent_forward(const float* z_all, int64_t B, int64_t R, int64_t D, int64_t replica_id,
+                                     float temperature, float* logits_ab, float* lse, float* row_loss,
+                                     float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Integer index / one-hot construction (tf2/objective.py:64-69), bit-exact:
+ * labels_idx[i] = i + replica_id*B; labels [B][2*R*B]; masks [B][R*B]. Any may be NULL. */
+SIMCLR_API int simclr_ntxent_labels(int64_t B, int64_t R, int64_t replica_id, int64_t* labels_idx,
+                                    float* labels, float* masks, void* stream);
+
+/* Backward of the job loss (sum_r loss_r / R) w.r.t. this replica's `hidden`
+ * [2B][D].  lse_all is the all-gather of lse, layout [R][2][B].  Includes the
+ * key-side terms TF obtains through the backward of the all-reduce
+ * and the l2-normalise backward.  grad_scale = dL/d(row loss) (1/(B*R) in the step). */
+SIMCLR_API int simclr_ntxent_backward(const float* z_all, const float* lse_all, const float* inv_norm,
+                                      int hidden_norm, int64_t B, int64_t R, int64_t D, int64_t replica_id,
+                                      float temperature, float grad_scale, float* dhidden,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Contrastive accuracy / entropy (tf2/metrics.py:23-36) from logits_ab [B][G]
+ * with label column i + replica_id*B.  out [2 + 2*B] floats: out[0] = accuracy,
+ * out[1] = entropy, the rest is per-row scratch. */
+SIMCLR_API int simclr_contrast_metrics(const float* logits_ab, int64_t B, int64_t G, int64_t replica_id,
+                                       float* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Supervised head loss  (tf2/objective.py:27-32) and small dense helpers
+ * ------------------------------------------------------------------------- */
+
+/* logits [rows][classes]; labels one-hot [label_rows][classes], row r uses
+ * labels[r % label_rows] (tf2/run.py:600-602 concat([l,l])).  loss [1] = mean CE;
+ * dlogits = (softmax - labels) * grad_scale (nullable).
+ * loss must have room for 1 + rows floats (loss[1..] holds the per-row losses). */
+SIMCLR_API int simclr_softmax_xent(const float* logits, const float* labels, int64_t rows, int64_t label_rows,
+                                   int64_t classes, float grad_scale, float* loss, float* dlogits,
+                                   void* stream);
+SIMCLR_API int simclr_bias_add(float* y, const float* bias, int64_t rows, int64_t C, void* stream);
+SIMCLR_API int simclr_bias_grad(const float* dy, float* dbias, int64_t rows, int64_t C, void* stream);
+/* y += a*x  (weight-decay gradient of the supervised head, tf2/model.py:47-60). */
+SIMCLR_API int simclr_axpy(float a, const float* x, float* y, int64_t n, void* stream);
+/* out[0] = sum(x^2)/2  (tf.nn.l2_loss); out must have room for 257 floats (scratch). */
+SIMCLR_API int simclr_l2_loss(const float* x, int64_t n, float* out, void* stream);
+SIMCLR_API int simclr_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* a += b (gradient fan-in of the residual branches, tf2/resnet.py:382,487 backward). */
+SIMCLR_API int simclr_add_inplace(void* a, const void* b, int dtype, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * LARS  (tf2/lars_optimizer.py:83-137), multi-tensor, two launches per step
+ * ------------------------------------------------------------------------- */
+
+/* Device tables (built once by the host): per tensor w/g/v pointers, numel,
+ * flags (bit0: weight decay applies, bit1: layer adaptation applies -- the
+ * name filters of tf2/lars_optimizer.py:139-157 evaluated by the host);
+ * per chunk (chunk_elems elements): tensor index and element offset;
+ * tensor_chunk_begin [n_tensors+1].  lr is a device scalar (lr_t).
+ * partials: scratch [n_chunks][2] floats.  Deterministic reduction order, so
+ * every replica applies bit-identical updates. */
+SIMCLR_API int simclr_lars_apply(int64_t n_tensors, int64_t n_chunks, const void* w_ptrs, const void* g_ptrs,
+                                 const void* v_ptrs, const int64_t* numels, const int32_t* flags,
+                                 const int32_t* chunk_tensor, const int64_t* chunk_offset,
+                                 const int64_t* tensor_chunk_begin, int64_t chunk_elems, const float* lr,
+                                 float momentum, float weight_decay, float eeta, float* partials,
+                                 void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * BatchNorm family  (tf2/resnet.py:31-78; formulas SURVEY.md A4)
+ * All tensors are [rows][C] views of NHWC activations (rows = N*H*W).
+ * ------------------------------------------------------------------------- */
+
+/* sums [2][C] doubles: sum x, sum x^2 over rows (zeroed by the call). */
+SIMCLR_API int simclr_bn_stats(const void* x, int dtype, int64_t rows, int64_t C, double* sums, void* stream);
+
+/* From (all-reduced) sums and the global element count: mean, rstd, fused
+ * scale = gamma*rstd and shift = beta - mean*scale; moving statistics update
+ * m <- m - (m - batch)*(1-momentum) with the biased variance.
+ * gamma/beta may be NULL (scale=False / center=False, tf2/model.py:135). */
+SIMCLR_API int simclr_bn_finalize(const double* sums, double count, const float* gamma, const float* beta,
+                                  float eps, float momentum, float* moving_mean, float* moving_var,
+                                  float* mean, float* rstd, float* scale, float* shift, int64_t C,
+                                  void* stream);
+
+/* z = act(y*scale + shift (+ residual)); relu: tf2/resnet.py:76-77,382,487. */
+SIMCLR_API int simclr_bn_apply(const void* y, int y_dtype, const void* residual, void* z, int z_dtype,
+                               int64_t rows, int64_t C, const float* scale, const float* shift, int relu,
+                               void* stream);
+
+/* Backward, phase 1.  dz <- (dz (+ dz2)) * [z > 0 if relu_mask_z != NULL] in
+ * place; sums [2][C] doubles: sum dz, sum dz*xhat with xhat=(y-mean)*rstd. */
+SIMCLR_API int simclr_bn_bwd_reduce(void* dz, const void* dz2, const void* relu_mask_z, int dtype,
+                                    const void* y, int y_dtype, int64_t rows, int64_t C, const float* mean,
+                                    const float* rstd, double* sums, void* stream);
+
+/* Backward, phase 2.  dy = gamma*rstd*(dz - S0/count - xhat*S1/count) with
+ * the (all-reduced) sums; dgamma/dbeta (nullable) are written from
+ * sums_local (this replica's contribution, summed later with the other grads). */
+SIMCLR_API int simclr_bn_bwd_apply(const void* dz, int dtype, const void* y, int y_dtype, void* dy,
+                                   int dy_dtype, int64_t rows, int64_t C, const float* mean,
+                                   const float* rstd, const float* gamma, const double* sums,
+                                   const double* sums_local, double count, float* dgamma, float* dbeta,
+                                   float* coef_ws /* scratch [3][C] */, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Pooling  (tf2/resnet.py:605-611 MaxPooling2D(3,2,'SAME'); :693-696 mean)
+ * ------------------------------------------------------------------------- */
+SIMCLR_API int simclr_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, int dtype, int64_t N,
+                                       int64_t H, int64_t W, int64_t C, void* stream);
+SIMCLR_API int simclr_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int dtype, int64_t N,
+                                       int64_t H, int64_t W, int64_t C, void* stream);
+SIMCLR_API int simclr_global_avgpool_fwd(const void* x, int dtype, void* y, int y_dtype, int64_t N,
+                                         int64_t HW, int64_t C, void* stream);
+SIMCLR_API int simclr_global_avgpool_bwd(const void* dy, int dy_dtype, void* dx, int dtype, int64_t N,
+                                         int64_t HW, int64_t C, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Convolution / dense as implicit GEMM  (tf2/resnet.py:183-208 Conv2dFixedPadding,
+ * tf2/model.py:143-151 Dense = 1x1 conv on [rows,1,1,Cin])
+ *   x  [N,H,W,Cs]   Cs = stored channels (Cin, or 4 for the 3-channel stem)
+ *   y  [N,Ho,Wo,Cout], Ho = H (stride 1) or (H-1)/stride+1 with pad (k-1)/2
+ * ------------------------------------------------------------------------- */
+
+/* tcgen05 engine operands: K-major packed copies of the fp32 HWIO master.
+ *   wf [Cout][Kp]       k = (r*S+s)*Cs + c,   Kp = round_up(R*S*Cs, 128B/elt)
+ *   wd [Cin ][R*S*Cout] k = (r*S+s)*Cout + co (NULL: not needed, e.g. the stem) */
+SIMCLR_API int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, int64_t R,
+                                       int64_t S, int64_t Cin, int64_t Cs, int64_t Cout, int64_t Kp,
+                                       void* stream);
+SIMCLR_API int simclr_conv2d_fprop_tc(const void* x, const void* wf, void* y, int dtype, int y_dtype,
+                                      int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cout, int64_t R,
+                                      int64_t S, int64_t stride, void* stream);
+SIMCLR_API int simclr_conv2d_dgrad_tc(const void* dy, const void* wd, void* dx, int dtype, int dx_dtype,
+                                      int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t R,
+                                      int64_t S, int64_t stride, void* stream);
+/* dw: fp32 HWIO [R][S][Cin][Cout], overwritten. */
+SIMCLR_API int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, int64_t N,
+                                      int64_t H, int64_t W, int64_t Cs, int64_t Cin, int64_t Cout, int64_t R,
+                                      int64_t S, int64_t stride, void* stream);
+
+/* CUDA-core fp32 engine reading the fp32 HWIO master directly (verification
+ * engine for the tcgen05 path; not the default). */
+SIMCLR_API int simclr_conv2d_fprop_simt(const void* x, const float* w_hwio, void* y, int dtype, int y_dtype,
+                                        int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cin,
+                                        int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream);
+SIMCLR_API int simclr_conv2d_dgrad_simt(const void* dy, const float* w_hwio, void* dx, int dtype,
+                                        int dx_dtype, int64_t N, int64_t H, int64_t W, int64_t Cin,
+                                        int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream);
+SIMCLR_API int simclr_conv2d_wgrad_simt(const void* x, const void* dy, float* dw, int dtype, int64_t N,
+                                        int64_t H, int64_t W, int64_t Cs, int64_t Cin, int64_t Cout,
+                                        int64_t R, int64_t S, int64_t stride, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Input preparation: split views, batch_random_blur, cast, pad 3->4 channels
+ * (tf2/model.py:250-259, tf2/data_util.py:323-361,393-440)
+ *   features [B,H,W,3*T] fp32 in [0,1]  ->  out [T*B,H,W,4] (view-major)
+ *   sigma [T] device floats; selector [T][B] device bytes; tmp [T*B,H,W,3] fp32.
+ * ------------------------------------------------------------------------- */
+SIMCLR_API int simclr_input_prep(const float* features, void* out, int dtype, int64_t B, int64_t H,
+                                 int64_t W, int64_t T, int use_blur, int64_t blur_kernel_size,
+                                 const float* sigma, const uint8_t* selector, float* tmp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMCLR_B200_H_ */

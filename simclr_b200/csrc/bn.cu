@@ -1,0 +1,336 @@
+// BatchNorm family (tf2/resnet.py:31-78).  All HBM-bound:
+// 16-byte vector loads, per-thread fp32 partials, block tree in shared memory,
+// one double atomicAdd per channel per block.  Tensors are [rows][C] views of
+// NHWC activations; C % 8 == 0.
+#include "common.cuh"
+
+namespace simclr {
+namespace {
+
+constexpr int BT = 256;
+
+template <typename T> __device__ __forceinline__ void load8(const T* p, float* f);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float* f) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
+  Vec16<__nv_bfloat16> v; v.load(p); v.unpack(f);
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float* f);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
+  Vec16<__nv_bfloat16> v; v.pack(f); v.store(p);
+}
+
+// Thread layout shared by the two reduction kernels: P threads span the
+// channel vectors of a row (power of two <= 256), 256/P "row lanes".
+struct RedLayout { int P, row_lanes, col_iters; };
+inline RedLayout red_layout(int64_t C) {
+  const int cvecs = (int)(C / 8);
+  int P = 1;
+  while (P * 2 <= cvecs && P * 2 <= BT) P *= 2;
+  RedLayout l; l.P = P; l.row_lanes = BT / P; l.col_iters = (cvecs + P - 1) / P;
+  return l;
+}
+
+// mode 0: stats (sum x, sum x^2).  mode 1: bwd reduce (sum dz, sum dz*xhat) with
+// optional in-place dz <- (dz + dz2) * [z > 0].
+template <typename T, typename Ty, int MODE>
+__global__ void __launch_bounds__(BT)
+bn_reduce_kernel(T* __restrict__ a, const T* __restrict__ a2, const T* __restrict__ zmask,
+                 const Ty* __restrict__ y, int64_t rows, int C, int P, int rows_per_block,
+                 const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ sums) {
+  extern __shared__ float sh[];   // [row_lanes][P*8][2]
+  const int tx = threadIdx.x % P, ty = threadIdx.x / P;
+  const int row_lanes = BT / P;
+  const int cvecs = C / 8;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  for (int cv = tx; cv < cvecs + (P - 1 - ((cvecs - 1) % P)); cv += P) {   // uniform trip count across tx
+    const bool active = cv < cvecs;
+    float s0[8], s1[8], mu[8], rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = 0.f; mu[i] = 0.f; rs[i] = 1.f; }
+    if (MODE == 1 && active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { mu[i] = mean[cv * 8 + i]; rs[i] = rstd[cv * 8 + i]; }
+    }
+    if (active) {
+      for (int64_t r = r0 + ty; r < r1; r += row_lanes) {
+        const int64_t off = r * C + (int64_t)cv * 8;
+        float v[8];
+        load8<T>(a + off, v);
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s0[i] += v[i]; s1[i] = fmaf(v[i], v[i], s1[i]); }
+        } else {
+          bool dirty = false;
+          if (a2 != nullptr) {
+            float w[8]; load8<T>(a2 + off, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += w[i];
+            dirty = true;
+          }
+          if (zmask != nullptr) {
+            float z[8]; load8<T>(zmask + off, z);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (z[i] > 0.f) ? v[i] : 0.f;
+            dirty = true;
+          }
+          if (dirty) {
+            store8<T>(a + off, v);
+            // keep the sums consistent with what phase 2 will read back
+            if (sizeof(T) == 2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = to_f<T>(from_f<T>(v[i]));
+            }
+          }
+          float yy[8]; load8<Ty>(y + off, yy);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = (yy[i] - mu[i]) * rs[i];
+            s0[i] += v[i];
+            s1[i] = fmaf(v[i], xh, s1[i]);
+          }
+        }
+      }
+    }
+    // block tree over row lanes
+    __syncthreads();
+    float* mine = sh + ((size_t)ty * P + tx) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mine[i] = s0[i]; mine[8 + i] = s1[i]; }
+    __syncthreads();
+    // P*16 values to reduce over row_lanes; thread t handles value index t, t+BT, ...
+    for (int idx = threadIdx.x; idx < P * 16; idx += BT) {
+      const int px = idx / 16, e = idx % 16;
+      const int c8 = (cv - tx + px);
+      if (c8 >= cvecs) continue;
+      double acc = 0.0;
+      for (int l = 0; l < row_lanes; ++l) acc += (double)sh[((size_t)l * P + px) * 16 + e];
+      const int ch = c8 * 8 + (e & 7);
+      atomicAdd(&sums[(e >> 3) * C + ch], acc);
+    }
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ mm, float* __restrict__ mv, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c] / count;
+  double var = sums[C + c] / count - m * m;      // biased variance (SyncBN form, A4)
+  if (var < 0.0) var = 0.0;
+  const float mf = (float)m, vf = (float)var;
+  const float r = rsqrtf(vf + eps);
+  const float g = gamma ? gamma[c] : 1.f;
+  const float b = beta ? beta[c] : 0.f;
+  const float sc = g * r;
+  mean[c] = mf; rstd[c] = r; scale[c] = sc; shift[c] = b - mf * sc;
+  if (mm) mm[c] = mm[c] - (mm[c] - mf) * (1.f - momentum);
+  if (mv) mv[c] = mv[c] - (mv[c] - vf) * (1.f - momentum);
+}
+
+template <typename Ty, typename Tz>
+__global__ void __launch_bounds__(BT)
+bn_apply_kernel(const Ty* __restrict__ y, const Tz* __restrict__ res, Tz* __restrict__ z, int64_t nvec, int C,
+                const float* __restrict__ scale, const float* __restrict__ shift, int relu) {
+  for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * BT) {
+    const int64_t off = i * 8;
+    const int c = (int)(off % C);
+    float v[8];
+    load8<Ty>(y + off, v);
+    const float4 sa = *reinterpret_cast<const float4*>(scale + c), sb = *reinterpret_cast<const float4*>(scale + c + 4);
+    const float4 ha = *reinterpret_cast<const float4*>(shift + c), hb = *reinterpret_cast<const float4*>(shift + c + 4);
+    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+    const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+    if (res != nullptr) {
+      float r[8]; load8<Tz>(res + off, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    store8<Tz>(z + off, v);
+  }
+}
+
+// dy = k1*dz + k2*y + k3 per channel, with
+//   k1 = gamma*rstd, k2 = -gamma*rstd^2*S1/M, k3 = gamma*rstd*(mean*rstd*S1/M - S0/M)
+// (== gamma*rstd*(dz - S0/M - xhat*S1/M)).
+__global__ void bn_bwd_coef_kernel(const float* __restrict__ mean, const float* __restrict__ rstd,
+                                   const float* __restrict__ gamma, const double* __restrict__ sums,
+                                   const double* __restrict__ sums_local, double inv_count,
+                                   float* __restrict__ coef, float* __restrict__ dgamma,
+                                   float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double r = rstd[c], mu = mean[c], g = gamma ? gamma[c] : 1.0;
+  const double a = sums[c] * inv_count, b = sums[C + c] * inv_count;
+  coef[c] = (float)(g * r);
+  coef[C + c] = (float)(-g * r * r * b);
+  coef[2 * C + c] = (float)(g * r * (mu * r * b - a));
+  if (dbeta) dbeta[c] = (float)sums_local[c];
+  if (dgamma) dgamma[c] = (float)sums_local[C + c];
+}
+
+template <typename T, typename Ty, typename Td>
+__global__ void __launch_bounds__(BT)
+bn_bwd_apply_kernel(const T* __restrict__ dz, const Ty* __restrict__ y, Td* __restrict__ dy, int64_t nvec, int C,
+                    const float* __restrict__ coef) {
+  for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * BT) {
+    const int64_t off = i * 8;
+    const int c = (int)(off % C);
+    float g[8], yy[8], o[8], k1[8], k2[8], k3[8];
+    load8<T>(dz + off, g);
+    load8<Ty>(y + off, yy);
+    load8<float>(coef + c, k1);
+    load8<float>(coef + C + c, k2);
+    load8<float>(coef + 2 * C + c, k3);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(k1[k], g[k], fmaf(k2[k], yy[k], k3[k]));
+    store8<Td>(dy + off, o);
+  }
+}
+
+inline unsigned ew_grid(int64_t nvec) {
+  int64_t b = (nvec + BT - 1) / BT;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+template <typename T, typename Ty, int MODE>
+int launch_reduce(void* a, const void* a2, const void* zmask, const void* y, int64_t rows, int64_t C,
+                  const float* mean, const float* rstd, double* sums, cudaStream_t st) {
+  const RedLayout l = red_layout(C);
+  int64_t nblocks = (rows + l.row_lanes * 8 - 1) / (l.row_lanes * 8);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (nblocks > cap) nblocks = cap;
+  if (nblocks < 1) nblocks = 1;
+  const int rows_per_block = (int)((rows + nblocks - 1) / nblocks);
+  nblocks = (rows + rows_per_block - 1) / rows_per_block;
+  const size_t smem = (size_t)BT * 16 * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st);
+  if (e != cudaSuccess) { set_error("bn reduce memset: %s", cudaGetErrorString(e)); return (int)e; }
+  bn_reduce_kernel<T, Ty, MODE><<<(unsigned)nblocks, BT, smem, st>>>(
+      (T*)a, (const T*)a2, (const T*)zmask, (const Ty*)y, rows, (int)C, l.P, rows_per_block, mean, rstd, sums);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+}  // namespace
+}  // namespace simclr
+
+using namespace simclr;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int simclr_bn_stats(const void* x, int dtype, int64_t rows, int64_t C, double* sums, void* stream) {
+  SIMCLR_CHECK_ARG(x && sums, "bn_stats: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_stats: need rows>0 and C%%8==0 (rows=%lld C=%lld)", (long long)rows, (long long)C);
+  SIMCLR_CHECK_ARG(aligned16(x), "bn_stats: x must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SIMCLR_F32) return launch_reduce<float, float, 0>((void*)x, nullptr, nullptr, nullptr, rows, C, nullptr, nullptr, sums, st);
+  if (dtype == SIMCLR_BF16) return launch_reduce<bf16, bf16, 0>((void*)x, nullptr, nullptr, nullptr, rows, C, nullptr, nullptr, sums, st);
+  set_error("bn_stats: unknown dtype %d", dtype);
+  return SIMCLR_ERR_INVALID_ARG;
+}
+
+int simclr_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,
+                       float momentum, float* moving_mean, float* moving_var, float* mean, float* rstd,
+                       float* scale, float* shift, int64_t C, void* stream) {
+  SIMCLR_CHECK_ARG(sums && mean && rstd && scale && shift, "bn_finalize: null pointer");
+  SIMCLR_CHECK_ARG(C > 0 && count > 0, "bn_finalize: bad C/count");
+  bn_finalize_kernel<<<(unsigned)((C + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      sums, count, gamma, beta, eps, momentum, moving_mean, moving_var, mean, rstd, scale, shift, (int)C);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_bn_apply(const void* y, int y_dtype, const void* residual, void* z, int z_dtype, int64_t rows,
+                    int64_t C, const float* scale, const float* shift, int relu, void* stream) {
+  SIMCLR_CHECK_ARG(y && z && scale && shift, "bn_apply: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_apply: need rows>0 and C%%8==0");
+  SIMCLR_CHECK_ARG(aligned16(y) && aligned16(z) && aligned16(residual), "bn_apply: pointers must be 16-byte aligned");
+  const int64_t nvec = rows * C / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = ew_grid(nvec);
+  if (y_dtype == SIMCLR_F32 && z_dtype == SIMCLR_F32)
+    bn_apply_kernel<float, float><<<grid, BT, 0, st>>>((const float*)y, (const float*)residual, (float*)z, nvec, (int)C, scale, shift, relu);
+  else if (y_dtype == SIMCLR_BF16 && z_dtype == SIMCLR_BF16)
+    bn_apply_kernel<bf16, bf16><<<grid, BT, 0, st>>>((const bf16*)y, (const bf16*)residual, (bf16*)z, nvec, (int)C, scale, shift, relu);
+  else if (y_dtype == SIMCLR_F32 && z_dtype == SIMCLR_BF16)
+    bn_apply_kernel<float, bf16><<<grid, BT, 0, st>>>((const float*)y, (const bf16*)residual, (bf16*)z, nvec, (int)C, scale, shift, relu);
+  else if (y_dtype == SIMCLR_BF16 && z_dtype == SIMCLR_F32)
+    bn_apply_kernel<bf16, float><<<grid, BT, 0, st>>>((const bf16*)y, (const float*)residual, (float*)z, nvec, (int)C, scale, shift, relu);
+  else { set_error("bn_apply: unknown dtypes %d/%d", y_dtype, z_dtype); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_bn_bwd_reduce(void* dz, const void* dz2, const void* relu_mask_z, int dtype, const void* y,
+                         int y_dtype, int64_t rows, int64_t C, const float* mean, const float* rstd,
+                         double* sums, void* stream) {
+  SIMCLR_CHECK_ARG(dz && y && mean && rstd && sums, "bn_bwd_reduce: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_bwd_reduce: need rows>0 and C%%8==0");
+  SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(dz2) && aligned16(relu_mask_z) && aligned16(y), "bn_bwd_reduce: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SIMCLR_F32 && y_dtype == SIMCLR_F32)
+    return launch_reduce<float, float, 1>(dz, dz2, relu_mask_z, y, rows, C, mean, rstd, sums, st);
+  if (dtype == SIMCLR_BF16 && y_dtype == SIMCLR_BF16)
+    return launch_reduce<bf16, bf16, 1>(dz, dz2, relu_mask_z, y, rows, C, mean, rstd, sums, st);
+  if (dtype == SIMCLR_BF16 && y_dtype == SIMCLR_F32)
+    return launch_reduce<bf16, float, 1>(dz, dz2, relu_mask_z, y, rows, C, mean, rstd, sums, st);
+  if (dtype == SIMCLR_F32 && y_dtype == SIMCLR_BF16)
+    return launch_reduce<float, bf16, 1>(dz, dz2, relu_mask_z, y, rows, C, mean, rstd, sums, st);
+  set_error("bn_bwd_reduce: unknown dtypes");
+  return SIMCLR_ERR_INVALID_ARG;
+}
+
+int simclr_bn_bwd_apply(const void* dz, int dtype, const void* y, int y_dtype, void* dy, int dy_dtype,
+                        int64_t rows, int64_t C, const float* mean, const float* rstd, const float* gamma,
+                        const double* sums, const double* sums_local, double count, float* dgamma,
+                        float* dbeta, float* coef_ws, void* stream) {
+  SIMCLR_CHECK_ARG(dz && y && dy && mean && rstd && sums && sums_local && coef_ws, "bn_bwd_apply: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && count > 0, "bn_bwd_apply: bad shape");
+  SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(y) && aligned16(dy), "bn_bwd_apply: alignment");
+  const int64_t nvec = rows * C / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = ew_grid(nvec);
+  SIMCLR_CHECK_ARG(aligned16(coef_ws), "bn_bwd_apply: coef_ws alignment");
+  bn_bwd_coef_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(mean, rstd, gamma, sums, sums_local, 1.0 / count,
+                                                                   coef_ws, dgamma, dbeta, (int)C);
+  SIMCLR_CHECK_LAUNCH();
+#define LAUNCH(T, Ty, Td) bn_bwd_apply_kernel<T, Ty, Td><<<grid, BT, 0, st>>>((const T*)dz, (const Ty*)y, (Td*)dy, nvec, (int)C, coef_ws)
+  const int key = dtype * 4 + y_dtype * 2 + dy_dtype;
+  switch (key) {
+    case 0: LAUNCH(float, float, float); break;
+    case 1: LAUNCH(float, float, bf16); break;
+    case 2: LAUNCH(float, bf16, float); break;
+    case 3: LAUNCH(float, bf16, bf16); break;
+    case 4: LAUNCH(bf16, float, float); break;
+    case 5: LAUNCH(bf16, float, bf16); break;
+    case 6: LAUNCH(bf16, bf16, float); break;
+    case 7: LAUNCH(bf16, bf16, bf16); break;
+    default: set_error("bn_bwd_apply: unknown dtypes"); return SIMCLR_ERR_INVALID_ARG;
+  }
+#undef LAUNCH
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,350 @@
+// Small kernels around the hot path: supervised-head loss, bias, weight
+// packing for the tcgen05 engine, input preparation (view split + Gaussian
+// blur + cast + channel pad), error plumbing.
+#include "common.cuh"
+
+namespace simclr {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+// one warp per row: loss_row = lse - sum(labels*logits); dlogits = (softmax - labels)*scale
+__global__ void softmax_xent_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                                    int64_t rows, int64_t label_rows, int classes, float grad_scale,
+                                    float* __restrict__ row_loss, float* __restrict__ dlogits) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* x = logits + r * classes;
+  const float* l = labels + (r % label_rows) * classes;
+  float m = -INFINITY;
+  for (int c = lane; c < classes; c += 32) m = fmaxf(m, x[c]);
+  m = warp_max(m);
+  float s = 0.f, dot = 0.f;
+  for (int c = lane; c < classes; c += 32) { s += expf(x[c] - m); dot = fmaf(l[c], x[c], dot); }
+  s = warp_sum(s); dot = warp_sum(dot);
+  const float lse = m + logf(s);
+  if (lane == 0) row_loss[r] = lse - dot;
+  if (dlogits) {
+    const float inv = 1.f / s;
+    for (int c = lane; c < classes; c += 32)
+      dlogits[r * classes + c] = (expf(x[c] - m) * inv - l[c]) * grad_scale;
+  }
+}
+
+__global__ void mean_kernel(const float* __restrict__ x, int64_t n, float scale, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) out[0] = s * scale;
+  }
+}
+
+__global__ void bias_add_kernel(float* __restrict__ y, const float* __restrict__ b, int64_t total, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += b[i % C];
+}
+
+__global__ void bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int64_t rows, int C) {
+  // block per 32 channels, 8 row lanes; fixed reduction order
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < C) for (int64_t r = ry; r < rows; r += 8) s += dy[r * C + c];
+  sh[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x & 31];
+    db[c] = t;
+  }
+}
+
+__global__ void axpy_kernel(float a, const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], y[i]);
+}
+
+__global__ void l2_partial_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ part) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s = fmaf(x[i], x[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+  }
+}
+
+template <typename Ts, typename Td>
+__global__ void cast_kernel(const Ts* __restrict__ s, Td* __restrict__ d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = from_f<Td>(to_f<Ts>(s[i]));
+}
+
+template <typename T>
+__global__ void add_inplace_kernel(T* __restrict__ a, const T* __restrict__ b, int64_t nvec) {
+  constexpr int V = Vec16<T>::N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    Vec16<T> x, y; x.load(a + i * V); y.load(b + i * V);
+    float fx[V], fy[V]; x.unpack(fx); y.unpack(fy);
+#pragma unroll
+    for (int k = 0; k < V; ++k) fx[k] += fy[k];
+    x.pack(fx); x.store(a + i * V);
+  }
+}
+
+// fp32 HWIO [R][S][Cin][Cout] -> wf [Cout][Kp] (k=(r*S+s)*Cs+c, zero padded) and
+// wd [Cin][R*S*Cout] (k=(r*S+s)*Cout+co).
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int R,
+                                   int S, int Cin, int Cs, int Cout, int Kp) {
+  const int64_t nf = (int64_t)Cout * Kp;
+  const int64_t nd = wd ? (int64_t)Cin * R * S * Cout : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < nf) {
+      const int co = (int)(i / Kp), k = (int)(i % Kp);
+      const int tap = k / Cs, c = k % Cs;
+      float v = 0.f;
+      if (tap < R * S && c < Cin) v = w[((int64_t)tap * Cin + c) * Cout + co];
+      wf[i] = from_f<T>(v);
+    } else {
+      const int64_t j = i - nf;
+      const int kd = R * S * Cout;
+      const int ci = (int)(j / kd), k = (int)(j % kd);
+      const int tap = k / Cout, co = k % Cout;
+      wd[j] = from_f<T>(w[((int64_t)tap * Cin + ci) * Cout + co]);
+    }
+  }
+}
+
+// ---- input prep ------------------------------------------------------------
+constexpr int MAX_TAPS = 65;
+
+__device__ __forceinline__ void make_taps(float* wsm, int radius, float sigma) {
+  // tf2/data_util.py:338-343: exp(-x^2 / (2 sigma^2)), normalised
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i <= 2 * radius; ++i) {
+      const float x = (float)(i - radius);
+      const float v = expf(-(x * x) / (2.f * sigma * sigma));
+      wsm[i] = v; tot += v;
+    }
+    for (int i = 0; i <= 2 * radius; ++i) wsm[i] /= tot;
+  }
+  __syncthreads();
+}
+
+// horizontal pass: features [B,H,W,3T] view t -> tmp [T*B,H,W,3]
+__global__ void blur_h_kernel(const float* __restrict__ f, float* __restrict__ tmp, int64_t B, int H, int W, int T,
+                              int radius, const float* __restrict__ sigma, const uint8_t* __restrict__ sel) {
+  __shared__ float wsm[MAX_TAPS];
+  const int t = blockIdx.y;
+  make_taps(wsm, radius, sigma[t]);
+  const int64_t total = B * H * W;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(p % W);
+    const int64_t bh = p / W;           // b*H + h
+    const int64_t b = bh / H;
+    if (!sel[(int64_t)t * B + b]) continue;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int i = -radius; i <= radius; ++i) {
+      const int ww = w + i;
+      if (ww < 0 || ww >= W) continue;       // zero 'SAME' padding
+      const float* src = f + (bh * W + ww) * (int64_t)(3 * T) + 3 * t;
+      const float k = wsm[i + radius];
+      a0 = fmaf(k, src[0], a0); a1 = fmaf(k, src[1], a1); a2 = fmaf(k, src[2], a2);
+    }
+    float* dst = tmp + (((int64_t)t * B * H + bh) * W + w) * 3;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2;
+  }
+}
+
+// vertical pass + per-sample select + clip + cast + pad to 4 channels
+template <typename To>
+__global__ void blur_v_kernel(const float* __restrict__ f, const float* __restrict__ tmp, To* __restrict__ out,
+                              int64_t B, int H, int W, int T, int radius, const float* __restrict__ sigma,
+                              const uint8_t* __restrict__ sel, int use_blur) {
+  __shared__ float wsm[MAX_TAPS];
+  const int t = blockIdx.y;
+  if (use_blur) make_taps(wsm, radius, sigma[t]);
+  const int64_t total = B * H * W;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(p % W);
+    const int64_t bh = p / W;
+    const int h = (int)(bh % H);
+    const int64_t b = bh / H;
+    float a0, a1, a2;
+    if (use_blur && sel[(int64_t)t * B + b]) {
+      a0 = a1 = a2 = 0.f;
+      for (int i = -radius; i <= radius; ++i) {
+        const int hh = h + i;
+        if (hh < 0 || hh >= H) continue;
+        const float* src = tmp + ((((int64_t)t * B + b) * H + hh) * W + w) * 3;
+        const float k = wsm[i + radius];
+        a0 = fmaf(k, src[0], a0); a1 = fmaf(k, src[1], a1); a2 = fmaf(k, src[2], a2);
+      }
+    } else {
+      const float* src = f + p * (int64_t)(3 * T) + 3 * t;
+      a0 = src[0]; a1 = src[1]; a2 = src[2];
+    }
+    if (use_blur) {   // tf.clip_by_value(images, 0., 1.)  (tf2/data_util.py:437)
+      a0 = fminf(fmaxf(a0, 0.f), 1.f); a1 = fminf(fmaxf(a1, 0.f), 1.f); a2 = fminf(fmaxf(a2, 0.f), 1.f);
+    }
+    To* dst = out + (((int64_t)t * B * H + bh) * W + w) * 4;
+    dst[0] = from_f<To>(a0); dst[1] = from_f<To>(a1); dst[2] = from_f<To>(a2); dst[3] = from_f<To>(0.f);
+  }
+}
+
+inline unsigned grid_for(int64_t total, int threads) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace
+}  // namespace simclr
+
+using namespace simclr;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int simclr_version(void) { return 100; }
+const char* simclr_last_error(void) { return g_err; }
+
+int simclr_softmax_xent(const float* logits, const float* labels, int64_t rows, int64_t label_rows,
+                        int64_t classes, float grad_scale, float* loss, float* dlogits, void* stream) {
+  SIMCLR_CHECK_ARG(logits && labels && loss, "softmax_xent: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && label_rows > 0 && classes > 0, "softmax_xent: bad shape");
+  // row losses are staged in dlogits' tail?  No: use a small static scratch via loss+1.. -> caller gives loss[1+rows]
+  cudaStream_t st = (cudaStream_t)stream;
+  float* row_loss = loss + 1;
+  softmax_xent_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, labels, rows, label_rows, (int)classes, grad_scale, row_loss, dlogits);
+  SIMCLR_CHECK_LAUNCH();
+  mean_kernel<<<1, 1024, 0, st>>>(row_loss, rows, 1.f / (float)rows, loss);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_bias_add(float* y, const float* bias, int64_t rows, int64_t C, void* stream) {
+  SIMCLR_CHECK_ARG(y && bias && rows > 0 && C > 0, "bias_add: bad args");
+  bias_add_kernel<<<grid_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(y, bias, rows * C, (int)C);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_bias_grad(const float* dy, float* dbias, int64_t rows, int64_t C, void* stream) {
+  SIMCLR_CHECK_ARG(dy && dbias && rows > 0 && C > 0, "bias_grad: bad args");
+  bias_grad_kernel<<<(unsigned)((C + 31) / 32), 256, 0, (cudaStream_t)stream>>>(dy, dbias, rows, (int)C);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_axpy(float a, const float* x, float* y, int64_t n, void* stream) {
+  SIMCLR_CHECK_ARG(x && y && n > 0, "axpy: bad args");
+  axpy_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, x, y, n);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_l2_loss(const float* x, int64_t n, float* out, void* stream) {
+  SIMCLR_CHECK_ARG(x && out && n > 0, "l2_loss: bad args");
+  // out needs 1 + 256 floats: out[0] result, out[1..] per-block partials
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (n + 1023) / 1024; if (blocks > 256) blocks = 256;
+  l2_partial_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, out + 1);
+  SIMCLR_CHECK_LAUNCH();
+  mean_kernel<<<1, 256, 0, st>>>(out + 1, blocks, 0.5f, out);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {
+  SIMCLR_CHECK_ARG(src && dst && n > 0, "cast: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = grid_for(n, 256);
+  if (src_dtype == SIMCLR_F32 && dst_dtype == SIMCLR_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+  else if (src_dtype == SIMCLR_BF16 && dst_dtype == SIMCLR_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+  else if (src_dtype == SIMCLR_F32 && dst_dtype == SIMCLR_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (src_dtype == SIMCLR_BF16 && dst_dtype == SIMCLR_BF16) cast_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+  else { set_error("cast: unknown dtypes"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_add_inplace(void* a, const void* b, int dtype, int64_t n, void* stream) {
+  SIMCLR_CHECK_ARG(a && b && n > 0, "add_inplace: bad args");
+  SIMCLR_CHECK_ARG(aligned16(a) && aligned16(b), "add_inplace: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SIMCLR_F32) {
+    SIMCLR_CHECK_ARG(n % 4 == 0, "add_inplace: n must be a multiple of 4");
+    add_inplace_kernel<float><<<grid_for(n / 4, 256), 256, 0, st>>>((float*)a, (const float*)b, n / 4);
+  } else if (dtype == SIMCLR_BF16) {
+    SIMCLR_CHECK_ARG(n % 8 == 0, "add_inplace: n must be a multiple of 8");
+    add_inplace_kernel<bf16><<<grid_for(n / 8, 256), 256, 0, st>>>((bf16*)a, (const bf16*)b, n / 8);
+  } else { set_error("add_inplace: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, int64_t R, int64_t S, int64_t Cin,
+                            int64_t Cs, int64_t Cout, int64_t Kp, void* stream) {
+  SIMCLR_CHECK_ARG(w_hwio && wf, "pack_conv_weight: null pointer");
+  SIMCLR_CHECK_ARG(R > 0 && S > 0 && Cin > 0 && Cs >= Cin && Cout > 0 && Kp >= R * S * Cs, "pack_conv_weight: bad shape");
+  SIMCLR_CHECK_ARG(wd == nullptr || Cs == Cin, "pack_conv_weight: dgrad copy needs Cs == Cin");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = Cout * Kp + (wd ? Cin * R * S * Cout : 0);
+  const unsigned grid = grid_for(total, 256);
+  if (dtype == SIMCLR_BF16) pack_weight_kernel<bf16><<<grid, 256, 0, st>>>(w_hwio, (bf16*)wf, (bf16*)wd, (int)R, (int)S, (int)Cin, (int)Cs, (int)Cout, (int)Kp);
+  else if (dtype == SIMCLR_F32) pack_weight_kernel<float><<<grid, 256, 0, st>>>(w_hwio, (float*)wf, (float*)wd, (int)R, (int)S, (int)Cin, (int)Cs, (int)Cout, (int)Kp);
+  else { set_error("pack_conv_weight: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_input_prep(const float* features, void* out, int dtype, int64_t B, int64_t H, int64_t W, int64_t T,
+                      int use_blur, int64_t blur_kernel_size, const float* sigma, const uint8_t* selector,
+                      float* tmp, void* stream) {
+  SIMCLR_CHECK_ARG(features && out, "input_prep: null pointer");
+  SIMCLR_CHECK_ARG(B > 0 && H > 0 && W > 0 && T > 0, "input_prep: bad shape");
+  const int radius = (int)(blur_kernel_size / 2);     // tf.cast(kernel_size / 2, int32), tf2/data_util.py:338
+  if (use_blur) {
+    SIMCLR_CHECK_ARG(sigma && selector && tmp, "input_prep: blur needs sigma, selector, tmp");
+    SIMCLR_CHECK_ARG(2 * radius + 1 <= MAX_TAPS, "input_prep: blur kernel too large (%d taps > %d)", 2 * radius + 1, MAX_TAPS);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = B * H * W;
+  int64_t bx = (total + 255) / 256; const int64_t cap = (int64_t)num_sms() * 8; if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, (unsigned)T);
+  if (use_blur) {
+    blur_h_kernel<<<grid, 256, 0, st>>>(features, tmp, B, (int)H, (int)W, (int)T, radius, sigma, selector);
+    SIMCLR_CHECK_LAUNCH();
+  }
+  if (dtype == SIMCLR_F32) blur_v_kernel<float><<<grid, 256, 0, st>>>(features, tmp, (float*)out, B, (int)H, (int)W, (int)T, radius, sigma, selector, use_blur);
+  else if (dtype == SIMCLR_BF16) blur_v_kernel<bf16><<<grid, 256, 0, st>>>(features, tmp, (bf16*)out, B, (int)H, (int)W, (int)T, radius, sigma, selector, use_blur);
+  else { set_error("input_prep: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+}  // extern "C"

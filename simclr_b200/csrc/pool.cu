@@ -1,0 +1,204 @@
+// Pooling kernels: MaxPooling2D(3,2,'SAME') (tf2/resnet.py:605-611, SURVEY A3:
+// TF-SAME pads after first) and the global mean over H,W (tf2/resnet.py:693-696).
+#include "common.cuh"
+
+namespace simclr {
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ argmax, int64_t total,
+                   int H, int W, int C, int Ho, int Wo, int pb_h, int pb_w) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * V;
+    int64_t p = idx / cv;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int64_t n = p / Ho;
+    float best[V]; int arg[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { best[i] = -INFINITY; arg[i] = 0; }
+    bool first = true;
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int h = ho * 2 - pb_h + dh;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int w = wo * 2 - pb_w + dw;
+        if (w < 0 || w >= W) continue;
+        Vec16<T> v; v.load(x + (((n * H + h) * W + w) * (int64_t)C + c));
+        float f[V]; v.unpack(f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          // first maximum in window scan order wins (matches TF / torch argmax routing)
+          if (first || f[i] > best[i]) { best[i] = f[i]; arg[i] = dh * 3 + dw; }
+        }
+        first = false;
+      }
+    }
+    Vec16<T> o; o.pack(best);
+    const int64_t ooff = ((n * Ho + ho) * Wo + wo) * (int64_t)C + c;
+    o.store(y + ooff);
+#pragma unroll
+    for (int i = 0; i < V; ++i) argmax[ooff + i] = (uint8_t)arg[i];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ argmax, T* __restrict__ dx,
+                   int64_t total, int H, int W, int C, int Ho, int Wo, int pb_h, int pb_w) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * V;
+    int64_t p = idx / cv;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int64_t n = p / H;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    // windows (ho,wo) with ho*2 - pb + dh == h, dh in 0..2
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int t = h + pb_h - dh;
+      if (t < 0 || (t & 1)) continue;
+      const int ho = t >> 1;
+      if (ho >= Ho) continue;
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int u = w + pb_w - dw;
+        if (u < 0 || (u & 1)) continue;
+        const int wo = u >> 1;
+        if (wo >= Wo) continue;
+        const int64_t ooff = ((n * Ho + ho) * Wo + wo) * (int64_t)C + c;
+        Vec16<T> g; g.load(dy + ooff);
+        float f[V]; g.unpack(f);
+        const int code = dh * 3 + dw;
+#pragma unroll
+        for (int i = 0; i < V; ++i) if (argmax[ooff + i] == code) acc[i] += f[i];
+      }
+    }
+    Vec16<T> o; o.pack(acc);
+    o.store(dx + (((n * H + h) * W + w) * (int64_t)C + c));
+  }
+}
+
+// x [N][HW][C] -> y [N][C] mean.  One thread per (n, channel); HW strided reads are
+// coalesced across channels.
+template <typename T, typename To>
+__global__ void avgpool_fwd_kernel(const T* __restrict__ x, To* __restrict__ y, int64_t N, int HW, int C) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * C) return;
+  const int64_t n = idx / C; const int c = (int)(idx % C);
+  const T* p = x + n * HW * (int64_t)C + c;
+  float s = 0.f;
+  for (int i = 0; i < HW; ++i) s += to_f<T>(p[(int64_t)i * C]);
+  y[idx] = from_f<To>(s / (float)HW);
+}
+
+template <typename Ti, typename T>
+__global__ void avgpool_bwd_kernel(const Ti* __restrict__ dy, T* __restrict__ dx, int64_t total, int HW, int C) {
+  const float inv = 1.f / (float)HW;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t n = idx / ((int64_t)HW * C);
+    dx[idx] = from_f<T>(to_f<Ti>(dy[n * C + c]) * inv);
+  }
+}
+
+inline void same_pad(int64_t H, int64_t* Ho, int* pb) {
+  *Ho = (H + 1) / 2;
+  int64_t total = (*Ho - 1) * 2 + 3 - H;
+  if (total < 0) total = 0;
+  *pb = (int)(total / 2);
+}
+inline unsigned grid_for(int64_t total, int threads) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace
+}  // namespace simclr
+
+using namespace simclr;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int simclr_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, int dtype, int64_t N, int64_t H, int64_t W,
+                            int64_t C, void* stream) {
+  SIMCLR_CHECK_ARG(x && y && argmax, "maxpool_fwd: null pointer");
+  SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool_fwd: need C%%8==0 and positive dims");
+  int64_t Ho, Wo; int pbh, pbw;
+  same_pad(H, &Ho, &pbh); same_pad(W, &Wo, &pbw);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SIMCLR_F32) {
+    const int64_t total = N * Ho * Wo * (C / 4);
+    maxpool_fwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, argmax, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw);
+  } else if (dtype == SIMCLR_BF16) {
+    const int64_t total = N * Ho * Wo * (C / 8);
+    maxpool_fwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, argmax, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw);
+  } else { set_error("maxpool_fwd: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int dtype, int64_t N, int64_t H,
+                            int64_t W, int64_t C, void* stream) {
+  SIMCLR_CHECK_ARG(dy && dx && argmax, "maxpool_bwd: null pointer");
+  SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool_bwd: need C%%8==0 and positive dims");
+  int64_t Ho, Wo; int pbh, pbw;
+  same_pad(H, &Ho, &pbh); same_pad(W, &Wo, &pbw);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SIMCLR_F32) {
+    const int64_t total = N * H * W * (C / 4);
+    maxpool_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)dy, argmax, (float*)dx, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw);
+  } else if (dtype == SIMCLR_BF16) {
+    const int64_t total = N * H * W * (C / 8);
+    maxpool_bwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)dy, argmax, (bf16*)dx, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw);
+  } else { set_error("maxpool_bwd: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_global_avgpool_fwd(const void* x, int dtype, void* y, int y_dtype, int64_t N, int64_t HW, int64_t C,
+                              void* stream) {
+  SIMCLR_CHECK_ARG(x && y && N > 0 && HW > 0 && C > 0, "avgpool_fwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((N * C + 255) / 256);
+  if (dtype == SIMCLR_F32 && y_dtype == SIMCLR_F32) avgpool_fwd_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, N, (int)HW, (int)C);
+  else if (dtype == SIMCLR_BF16 && y_dtype == SIMCLR_BF16) avgpool_fwd_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, N, (int)HW, (int)C);
+  else if (dtype == SIMCLR_BF16 && y_dtype == SIMCLR_F32) avgpool_fwd_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)x, (float*)y, N, (int)HW, (int)C);
+  else if (dtype == SIMCLR_F32 && y_dtype == SIMCLR_BF16) avgpool_fwd_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x, (bf16*)y, N, (int)HW, (int)C);
+  else { set_error("avgpool_fwd: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_global_avgpool_bwd(const void* dy, int dy_dtype, void* dx, int dtype, int64_t N, int64_t HW, int64_t C,
+                              void* stream) {
+  SIMCLR_CHECK_ARG(dy && dx && N > 0 && HW > 0 && C > 0, "avgpool_bwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = N * HW * C;
+  const unsigned grid = grid_for(total, 256);
+  if (dy_dtype == SIMCLR_F32 && dtype == SIMCLR_F32) avgpool_bwd_kernel<float, float><<<grid, 256, 0, st>>>((const float*)dy, (float*)dx, total, (int)HW, (int)C);
+  else if (dy_dtype == SIMCLR_BF16 && dtype == SIMCLR_BF16) avgpool_bwd_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)dy, (bf16*)dx, total, (int)HW, (int)C);
+  else if (dy_dtype == SIMCLR_F32 && dtype == SIMCLR_BF16) avgpool_bwd_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)dy, (bf16*)dx, total, (int)HW, (int)C);
+  else if (dy_dtype == SIMCLR_BF16 && dtype == SIMCLR_F32) avgpool_bwd_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)dy, (float*)dx, total, (int)HW, (int)C);
+  else { set_error("avgpool_bwd: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,665 @@
+// tcgen05 implicit-GEMM engine for conv fprop / dgrad / wgrad and the dense
+// layers (tf2/resnet.py:183-208, tf2/model.py:143-151).
+//
+// One persistent, warp-specialised kernel per GEMM flavour:
+//   warps 0-3  epilogue     TMEM -> registers (tcgen05.ld) -> global
+//   warp  4    MMA issuer   one elected lane issues tcgen05.mma, accumulators in TMEM
+//   warp  5    TMA producer weights / dY tiles (and activations for 1x1 stride-1)
+//   warps 6-9  gather       im2col rows of NHWC activations -> 128B-swizzled smem
+// Pipelines: smem full/empty mbarriers (producers <-> MMA) and a double-buffered
+// TMEM accumulator (MMA <-> epilogue), so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Tiles: 128 (TMEM lanes) x BN x 128 bytes of K per stage.
+#include "tc_common.cuh"
+
+namespace simclr {
+namespace tc {
+namespace {
+
+constexpr int A_STAGE_BYTES = 128 * 128;     // 128 rows x 128 B
+constexpr int PIPE_BYTES = 192 * 1024;
+constexpr int EPI_THREADS = 128;
+constexpr int GATHER_THREADS = 128;
+
+template <int BN> struct Tile {
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = PIPE_BYTES / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // double-buffered accumulator (power of 2)
+  static constexpr size_t SMEM_BYTES = 1024 /*align*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+};
+
+struct Geom {
+  const void* src;     // gathered tensor: X (fprop/wgrad) or dY (dgrad), NHWC
+  void* out;
+  int mode;            // 0: out pixel -> in pixel = p*stride - pad + r ; 1 (dgrad): (p + pad - r)/stride
+  int H, W, C;         // dims of the gathered tensor
+  int R, S, RS, stride, pad_h, pad_w;
+  FastDiv dPQ, dQ, dC, dS;
+  long long M;         // GEMM rows (pixels)
+  int n_out, ldc;      // valid output columns, output row stride (elements)
+  int num_kb;          // K blocks (fprop/dgrad) or pixel blocks (wgrad)
+  int tiles_m, tiles_n;
+  // wgrad only
+  int Cin, Cout, splits, kb_per_split;
+};
+
+template <typename T> struct Elt;
+template <> struct Elt<__nv_bfloat16> { static constexpr bool TF32 = false; static constexpr int KBE = 64; static constexpr int CH = 8; };
+template <> struct Elt<float> { static constexpr bool TF32 = true; static constexpr int KBE = 32; static constexpr int CH = 4; };
+
+struct Pipe { int stage; uint32_t phase; };
+template <int STAGES> __device__ __forceinline__ void advance(Pipe& p) {
+  if (++p.stage == STAGES) { p.stage = 0; p.phase ^= 1; }
+}
+
+// Address of the source pixel for GEMM-row bases (n, bh, bw) and filter tap (r, s); nullptr if padding.
+template <typename T>
+__device__ __forceinline__ const T* src_pixel(const Geom& g, int n, int bh, int bw, int r, int s) {
+  int h, w;
+  if (g.mode == 0) {
+    h = bh + r; w = bw + s;
+    if ((unsigned)h >= (unsigned)g.H || (unsigned)w >= (unsigned)g.W) return nullptr;
+  } else {
+    const int hh = bh - r, ww = bw - s;
+    if (hh < 0 || ww < 0) return nullptr;
+    if (g.stride == 1) { h = hh; w = ww; }
+    else if (g.stride == 2) { if ((hh | ww) & 1) return nullptr; h = hh >> 1; w = ww >> 1; }
+    else { if (hh % g.stride || ww % g.stride) return nullptr; h = hh / g.stride; w = ww / g.stride; }
+    if (h >= g.H || w >= g.W) return nullptr;
+  }
+  return reinterpret_cast<const T*>(g.src) + ((long long)(n * g.H + h) * g.W + w) * g.C;
+}
+
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint2 ldg8(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void sts16(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 16 bytes of K for one gathered row.  SMALLC (bf16, C == 4): the chunk holds two taps of 4 channels.
+template <typename T, bool SMALLC>
+__device__ __forceinline__ uint4 gather_chunk(const Geom& g, int n, int bh, int bw, uint32_t k0) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (n < 0) return v;
+  if (!SMALLC) {
+    uint32_t tap, c; g.dC.divmod(k0, tap, c);
+    if ((int)tap < g.RS) {
+      uint32_t r, s; g.dS.divmod(tap, r, s);
+      const T* p = src_pixel<T>(g, n, bh, bw, (int)r, (int)s);
+      if (p) v = ldg16(p + c);
+    }
+  } else {
+    const uint32_t tap0 = k0 >> 2;     // C == 4
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const uint32_t tap = tap0 + half;
+      if ((int)tap < g.RS) {
+        uint32_t r, s; g.dS.divmod(tap, r, s);
+        const T* p = src_pixel<T>(g, n, bh, bw, (int)r, (int)s);
+        if (p) { const uint2 u = ldg8(p); if (half == 0) { v.x = u.x; v.y = u.y; } else { v.z = u.x; v.w = u.y; } }
+      }
+    }
+  }
+  return v;
+}
+
+template <typename To>
+__device__ __forceinline__ void store_row32(To* dst, const uint32_t* acc, int valid, bool vec_ok);
+template <>
+__device__ __forceinline__ void store_row32<float>(float* dst, const uint32_t* acc, int valid, bool vec_ok) {
+  if (valid >= 32 && vec_ok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      reinterpret_cast<uint4*>(dst)[i] = make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) if (i < valid) dst[i] = __uint_as_float(acc[i]);
+  }
+}
+template <>
+__device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, const uint32_t* acc, int valid, bool vec_ok) {
+  if (valid >= 32 && vec_ok) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(acc[8 * i + 2 * j]), __uint_as_float(acc[8 * i + 2 * j + 1]));
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      reinterpret_cast<uint4*>(dst)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) if (i < valid) dst[i] = __float2bfloat16_rn(__uint_as_float(acc[i]));
+  }
+}
+
+struct SmemCtl {
+  uint64_t* full; uint64_t* empty; uint64_t* tmem_full; uint64_t* tmem_empty; uint32_t* tmem_ptr;
+};
+template <int STAGES>
+__device__ __forceinline__ SmemCtl carve(uint8_t* base, int stage_bytes) {
+  SmemCtl c;
+  uint64_t* b = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * stage_bytes);
+  c.full = b; c.empty = b + STAGES; c.tmem_full = b + 2 * STAGES; c.tmem_empty = b + 2 * STAGES + 2;
+  c.tmem_ptr = reinterpret_cast<uint32_t*>(b + 2 * STAGES + 4);
+  return c;
+}
+
+// ===========================================================================
+// fprop / dgrad / dense:  out[M][n_out] = gather(src)[M][K] * Wk[n_out][K]^T
+// ===========================================================================
+template <typename T, typename To, int BN, bool A_TMA, bool SMALLC>
+__global__ void __launch_bounds__(A_TMA ? 192 : 320, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Geom g) {
+  using TL = Tile<BN>;
+  constexpr int STAGES = TL::STAGES;
+  constexpr bool TF32 = Elt<T>::TF32;
+  constexpr int KBE = Elt<T>::KBE;
+  constexpr int CH = Elt<T>::CH;
+  constexpr uint32_t IDESC = make_idesc(TF32, 128, BN, false, false);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const SmemCtl ctl = carve<STAGES>(smem, TL::STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&ctl.full[s], A_TMA ? 1 : 1 + GATHER_THREADS);
+      mbar_init(&ctl.empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS); }
+    fence_barrier_init();
+  }
+  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmap_b); if (A_TMA) tma_prefetch_desc(&tmap_a); }
+  if (warp == 4) tmem_alloc(ctl.tmem_ptr, TL::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *ctl.tmem_ptr;
+  const int num_tiles = g.tiles_m * g.tiles_n;
+
+  if (warp < 4) {
+    // ------------------------------ epilogue ------------------------------
+    int as = 0; uint32_t aphase = 0;
+    To* out = reinterpret_cast<To*>(g.out);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((g.ldc * (int)sizeof(To)) % 16 == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / g.tiles_n, tn = tile - tm * g.tiles_n;
+      mbar_wait(&ctl.tmem_full[as], aphase, 10);
+      tc_fence_after();
+      const long long m = (long long)tm * 128 + warp * 32 + lane;
+      const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(tbase + c * 32, acc);
+        tmem_ld_wait();
+        const int n0 = tn * BN + c * 32;
+        const int valid = g.n_out - n0;
+        if (m < g.M && valid > 0) store_row32<To>(out + m * g.ldc + n0, acc, valid, vec_ok);
+      }
+      tc_fence_before();
+      mbar_arrive(&ctl.tmem_empty[as]);
+      as ^= 1; if (as == 0) aphase ^= 1;
+    }
+  } else if (warp == 4) {
+    // ------------------------------ MMA issuer ----------------------------
+    Pipe pp{0, 0};
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&ctl.tmem_empty[as], aphase ^ 1, 20);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      for (int kb = 0; kb < g.num_kb; ++kb) {
+        mbar_wait(&ctl.full[pp.stage], pp.phase, 21);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + (size_t)pp.stage * TL::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {      // 4 x (32 bytes of K) per stage
+            const uint64_t ad = smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma<TF32>(d_tmem, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&ctl.empty[pp.stage]);            // frees the smem slot when the MMAs retire
+          if (kb == g.num_kb - 1) umma_commit(&ctl.tmem_full[as]);
+        }
+        __syncwarp();
+        advance<STAGES>(pp);
+      }
+      as ^= 1; if (as == 0) aphase ^= 1;
+    }
+  } else if (warp == 5) {
+    // ------------------------------ TMA producer --------------------------
+    if (lane == 0) {
+      Pipe pp{0, 0};
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / g.tiles_n, tn = tile - tm * g.tiles_n;
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+          mbar_wait(&ctl.empty[pp.stage], pp.phase ^ 1, 30);
+          uint8_t* a_dst = smem + (size_t)pp.stage * TL::STAGE_BYTES;
+          mbar_arrive_expect_tx(&ctl.full[pp.stage], TL::B_STAGE_BYTES + (A_TMA ? A_STAGE_BYTES : 0));
+          if (A_TMA) tma_load_2d(a_dst, &tmap_a, &ctl.full[pp.stage], kb * KBE, tm * 128);
+          tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &ctl.full[pp.stage], kb * KBE, tn * BN);
+          advance<STAGES>(pp);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ gather producers ----------------------
+    if (!A_TMA) {
+      const int gt = threadIdx.x - 192;
+      const int j = gt & 7;              // 16-byte chunk within the 128-byte K block
+      const int row0 = gt >> 3;          // rows row0 + 16*i
+      Pipe pp{0, 0};
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / g.tiles_n;
+        int rn[8], rbh[8], rbw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long m = (long long)tm * 128 + row0 + 16 * i;
+          if (m < g.M) {
+            uint32_t n, rem, p, q;
+            g.dPQ.divmod((uint32_t)m, n, rem);
+            g.dQ.divmod(rem, p, q);
+            rn[i] = (int)n;
+            rbh[i] = g.mode == 0 ? (int)p * g.stride - g.pad_h : (int)p + g.pad_h;
+            rbw[i] = g.mode == 0 ? (int)q * g.stride - g.pad_w : (int)q + g.pad_w;
+          } else { rn[i] = -1; rbh[i] = 0; rbw[i] = 0; }
+        }
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+          const uint32_t k0 = (uint32_t)(kb * KBE + j * CH);
+          uint4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = gather_chunk<T, SMALLC>(g, rn[i], rbh[i], rbw[i], k0);
+          mbar_wait(&ctl.empty[pp.stage], pp.phase ^ 1, 40);
+          const uint32_t a_addr = smem_u32(smem + (size_t)pp.stage * TL::STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sts16(a_addr + sw128_offset(row0 + 16 * i, j), v[i]);
+          fence_proxy_async();
+          mbar_arrive(&ctl.full[pp.stage]);
+          advance<STAGES>(pp);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, TL::TMEM_COLS); }
+}
+
+// ===========================================================================
+// wgrad:  dW[(r,s,c)][co] = sum_pixels X[pixel@(r,s)][c] * dY[pixel][co]
+// A^T (activations) and B (dY) are both MN-major: the reduction runs over pixels.
+// Work item = (128 k-rows) x (BN couts) x (pixel split); fp32 atomics combine splits.
+// ===========================================================================
+template <typename T, int BN, bool SMALLC>
+__global__ void __launch_bounds__(320, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const Geom g, float* __restrict__ dw) {
+  using TL = Tile<BN>;
+  constexpr int STAGES = TL::STAGES;
+  constexpr bool TF32 = Elt<T>::TF32;
+  constexpr int ATOM_E = Elt<T>::KBE;            // elements along MN per 128-byte atom row
+  constexpr int CH = Elt<T>::CH;
+  constexpr int A_ATOMS = 128 / ATOM_E;          // 2 (bf16) / 4 (fp32)
+  constexpr int PXS = A_STAGE_BYTES / (A_ATOMS * 128);   // pixels per stage: 64 / 32
+  constexpr int UMMA_K = 32 / (int)sizeof(T);    // 16 / 8 pixels per MMA
+  constexpr int ATOM_BYTES = PXS * 128;
+  constexpr int B_ATOMS = BN / ATOM_E;
+  constexpr uint32_t IDESC = make_idesc(TF32, 128, BN, true, true);
+  static_assert(PXS / UMMA_K == 4, "4 MMAs per stage");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const SmemCtl ctl = carve<STAGES>(smem, TL::STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl.full[s], 1 + GATHER_THREADS); mbar_init(&ctl.empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS); }
+    fence_barrier_init();
+  }
+  if (warp == 5 && lane == 0) tma_prefetch_desc(&tmap_dy);
+  if (warp == 4) tmem_alloc(ctl.tmem_ptr, TL::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *ctl.tmem_ptr;
+  const int num_items = g.tiles_m * g.tiles_n * g.splits;   // tiles_m = k-row tiles
+
+  // item -> (tk, tn, split); splits of one tile are adjacent so their dY reads share L2
+  auto decode = [&](int item, int& tk, int& tn, int& kb0, int& kb1) {
+    const int split = item % g.splits;
+    const int t = item / g.splits;
+    tk = t / g.tiles_n; tn = t - tk * g.tiles_n;
+    kb0 = split * g.kb_per_split;
+    kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+  };
+
+  if (warp < 4) {
+    int as = 0; uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int tk, tn, kb0, kb1; decode(item, tk, tn, kb0, kb1);
+      if (kb0 >= kb1) continue;
+      mbar_wait(&ctl.tmem_full[as], aphase, 50);
+      tc_fence_after();
+      const int k = tk * 128 + warp * 32 + lane;           // row of the [R*S*Cs][Cout] matrix
+      uint32_t tap, c; g.dC.divmod((uint32_t)k, tap, c);
+      const bool row_ok = (int)tap < g.RS && (int)c < g.Cin;
+      float* drow = dw + ((long long)tap * g.Cin + c) * g.Cout;
+      const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t acc[32];
+        tmem_ld32(tbase + cc * 32, acc);
+        tmem_ld_wait();
+        const int n0 = tn * BN + cc * 32;
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (n0 + i < g.Cout) atomicAdd(drow + n0 + i, __uint_as_float(acc[i]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&ctl.tmem_empty[as]);
+      as ^= 1; if (as == 0) aphase ^= 1;
+    }
+  } else if (warp == 4) {
+    Pipe pp{0, 0};
+    int as = 0; uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int tk, tn, kb0, kb1; decode(item, tk, tn, kb0, kb1);
+      if (kb0 >= kb1) continue;
+      mbar_wait(&ctl.tmem_empty[as], aphase ^ 1, 60);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&ctl.full[pp.stage], pp.phase, 61);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + (size_t)pp.stage * TL::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // MN-major: LBO = distance between 128-byte-wide atoms along M/N, SBO = 8 pixel rows
+            const uint64_t ad = smem_desc_sw128(a_addr + k * UMMA_K * 128, ATOM_BYTES, 1024);
+            const uint64_t bd = smem_desc_sw128(b_addr + k * UMMA_K * 128, ATOM_BYTES, 1024);
+            umma<TF32>(d_tmem, ad, bd, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&ctl.empty[pp.stage]);
+          if (kb == kb1 - 1) umma_commit(&ctl.tmem_full[as]);
+        }
+        __syncwarp();
+        advance<STAGES>(pp);
+      }
+      as ^= 1; if (as == 0) aphase ^= 1;
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      Pipe pp{0, 0};
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int tk, tn, kb0, kb1; decode(item, tk, tn, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&ctl.empty[pp.stage], pp.phase ^ 1, 70);
+          uint8_t* b_dst = smem + (size_t)pp.stage * TL::STAGE_BYTES + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&ctl.full[pp.stage], TL::B_STAGE_BYTES);
+#pragma unroll
+          for (int a = 0; a < B_ATOMS; ++a)
+            tma_load_2d(b_dst + a * ATOM_BYTES, &tmap_dy, &ctl.full[pp.stage], tn * BN + a * ATOM_E, kb * PXS);
+          advance<STAGES>(pp);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int gt = threadIdx.x - 192;
+    const int j = gt & 7;
+    Pipe pp{0, 0};
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int tk, tn, kb0, kb1; decode(item, tk, tn, kb0, kb1);
+      // piece i of this thread: q = gt/8 + 16*i -> atom q / PXS, pixel q % PXS; its (tap, c) is fixed per item
+      int pr[8], ps[8], pc[8]; bool pk[8];
+      int pr2[8], ps2[8]; bool pk2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int q = (gt >> 3) + 16 * i;
+        const int atom = q / PXS;
+        const uint32_t k = (uint32_t)(tk * 128 + atom * ATOM_E + j * CH);
+        if (!SMALLC) {
+          uint32_t tap, c, r, s; g.dC.divmod(k, tap, c); g.dS.divmod(tap, r, s);
+          pk[i] = (int)tap < g.RS; pr[i] = (int)r; ps[i] = (int)s; pc[i] = (int)c;
+          pk2[i] = false; pr2[i] = ps2[i] = 0;
+        } else {
+          const uint32_t tap0 = k >> 2;
+          uint32_t r, s; g.dS.divmod(tap0, r, s);
+          pk[i] = (int)tap0 < g.RS; pr[i] = (int)r; ps[i] = (int)s; pc[i] = 0;
+          g.dS.divmod(tap0 + 1, r, s);
+          pk2[i] = (int)(tap0 + 1) < g.RS; pr2[i] = (int)r; ps2[i] = (int)s;
+        }
+      }
+      for (int kb = kb0; kb < kb1; ++kb) {
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int q = (gt >> 3) + 16 * i;
+          const int px = q % PXS;
+          const long long m = (long long)kb * PXS + px;
+          v[i] = make_uint4(0, 0, 0, 0);
+          if (m < g.M) {
+            uint32_t n, rem, p, qq;
+            g.dPQ.divmod((uint32_t)m, n, rem);
+            g.dQ.divmod(rem, p, qq);
+            const int bh = (int)p * g.stride - g.pad_h, bw = (int)qq * g.stride - g.pad_w;
+            if (!SMALLC) {
+              if (pk[i]) {
+                const T* src = src_pixel<T>(g, (int)n, bh, bw, pr[i], ps[i]);
+                if (src) v[i] = ldg16(src + pc[i]);
+              }
+            } else {
+              if (pk[i]) { const T* src = src_pixel<T>(g, (int)n, bh, bw, pr[i], ps[i]); if (src) { const uint2 u = ldg8(src); v[i].x = u.x; v[i].y = u.y; } }
+              if (pk2[i]) { const T* src = src_pixel<T>(g, (int)n, bh, bw, pr2[i], ps2[i]); if (src) { const uint2 u = ldg8(src); v[i].z = u.x; v[i].w = u.y; } }
+            }
+          }
+        }
+        mbar_wait(&ctl.empty[pp.stage], pp.phase ^ 1, 80);
+        const uint32_t a_addr = smem_u32(smem + (size_t)pp.stage * TL::STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int q = (gt >> 3) + 16 * i;
+          sts16(a_addr + (q / PXS) * ATOM_BYTES + sw128_offset(q % PXS, j), v[i]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&ctl.full[pp.stage]);
+        advance<STAGES>(pp);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, TL::TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+inline int pick_bn(int64_t n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
+
+template <typename K> int set_smem_attr(K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e)); return (int)e; }
+  return SIMCLR_OK;
+}
+
+template <typename T, typename To, int BN, bool A_TMA, bool SMALLC>
+int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, cudaStream_t st) {
+  auto kern = igemm_kernel<T, To, BN, A_TMA, SMALLC>;
+  static bool attr = false;
+  if (!attr) { int rc = set_smem_attr(kern, Tile<BN>::SMEM_BYTES); if (rc) return rc; attr = true; }
+  int grid = g.tiles_m * g.tiles_n; if (grid > num_sms()) grid = num_sms();
+  kern<<<grid, A_TMA ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(ta, tb, g);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+template <typename T, typename To, int BN>
+int dispatch_igemm2(bool a_tma, bool smallc, const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, cudaStream_t st) {
+  if (a_tma) return launch_igemm<T, To, BN, true, false>(ta, tb, g, st);
+  if (smallc) return launch_igemm<T, To, BN, false, true>(ta, tb, g, st);
+  return launch_igemm<T, To, BN, false, false>(ta, tb, g, st);
+}
+template <typename T, typename To>
+int dispatch_igemm(int bn, bool a_tma, bool smallc, const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, cudaStream_t st) {
+  if (bn == 256) return dispatch_igemm2<T, To, 256>(a_tma, smallc, ta, tb, g, st);
+  if (bn == 128) return dispatch_igemm2<T, To, 128>(a_tma, smallc, ta, tb, g, st);
+  return dispatch_igemm2<T, To, 64>(a_tma, smallc, ta, tb, g, st);
+}
+
+// Shared driver for fprop (mode 0) and dgrad (mode 1).
+//   gathered tensor [N][Hs][Ws][Cs]; GEMM rows = N*P*Q; weights wk [n_out][Kp]
+int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, int out_dtype, int64_t N, int64_t Hs,
+              int64_t Ws, int64_t Cs, int64_t P, int64_t Q, int64_t n_out, int64_t R, int64_t S, int64_t stride,
+              cudaStream_t st, const char* what) {
+  const int es = dtype == SIMCLR_BF16 ? 2 : 4;
+  const int KBE = 128 / es, CH = 16 / es;
+  const bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);
+  if (!(Cs % CH == 0 || smallc)) { set_error("%s: stored channels (%lld) must be a multiple of %d", what, (long long)Cs, CH); return SIMCLR_ERR_UNSUPPORTED; }
+  if (!aligned16(src) || !aligned16(wk)) { set_error("%s: operands must be 16-byte aligned", what); return SIMCLR_ERR_INVALID_ARG; }
+  const int64_t M = N * P * Q;
+  if (M >= (1ll << 31)) { set_error("%s: M too large", what); return SIMCLR_ERR_UNSUPPORTED; }
+  const int64_t K = R * S * Cs;
+  const int64_t Kp = (K + KBE - 1) / KBE * KBE;
+  const int bn = pick_bn(n_out);
+  Geom g;
+  g.src = src; g.out = out; g.mode = mode;
+  g.H = (int)Hs; g.W = (int)Ws; g.C = (int)Cs; g.R = (int)R; g.S = (int)S; g.RS = (int)(R * S);
+  g.stride = (int)stride; g.pad_h = (int)((R - 1) / 2); g.pad_w = (int)((S - 1) / 2);
+  g.dPQ = FastDiv((uint32_t)(P * Q)); g.dQ = FastDiv((uint32_t)Q); g.dC = FastDiv((uint32_t)Cs); g.dS = FastDiv((uint32_t)S);
+  g.M = M; g.n_out = (int)n_out; g.ldc = (int)n_out; g.num_kb = (int)(Kp / KBE);
+  g.tiles_m = (int)((M + 127) / 128); g.tiles_n = (int)((n_out + bn - 1) / bn);
+  g.Cin = g.Cout = 0; g.splits = 1; g.kb_per_split = g.num_kb;
+  // plain GEMM (1x1, stride 1, no padding): activations go through TMA as well
+  const bool a_tma = (R == 1 && S == 1 && stride == 1 && !smallc && (Cs * es) % 16 == 0);
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&tb, wk, es, (uint64_t)n_out, (uint64_t)Kp, (uint64_t)Kp * es, (uint32_t)bn, (uint32_t)KBE);
+  if (rc) return rc;
+  if (a_tma) { rc = make_tmap_2d(&ta, src, es, (uint64_t)M, (uint64_t)Cs, (uint64_t)Cs * es, 128, (uint32_t)KBE); if (rc) return rc; }
+  else ta = tb;
+  if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_BF16) return dispatch_igemm<__nv_bfloat16, __nv_bfloat16>(bn, a_tma, smallc, ta, tb, g, st);
+  if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_F32) return dispatch_igemm<__nv_bfloat16, float>(bn, a_tma, smallc, ta, tb, g, st);
+  if (dtype == SIMCLR_F32 && out_dtype == SIMCLR_F32) return dispatch_igemm<float, float>(bn, a_tma, smallc, ta, tb, g, st);
+  set_error("%s: unsupported dtype combination %d -> %d", what, dtype, out_dtype);
+  return SIMCLR_ERR_UNSUPPORTED;
+}
+
+template <typename T, int BN, bool SMALLC>
+int launch_wgrad(const CUtensorMap& tdy, const Geom& g, float* dw, cudaStream_t st) {
+  auto kern = wgrad_kernel<T, BN, SMALLC>;
+  static bool attr = false;
+  if (!attr) { int rc = set_smem_attr(kern, Tile<BN>::SMEM_BYTES); if (rc) return rc; attr = true; }
+  int grid = g.tiles_m * g.tiles_n * g.splits; if (grid > num_sms()) grid = num_sms();
+  kern<<<grid, 320, Tile<BN>::SMEM_BYTES, st>>>(tdy, g, dw);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+template <typename T>
+int dispatch_wgrad(int bn, bool smallc, const CUtensorMap& tdy, const Geom& g, float* dw, cudaStream_t st) {
+  if (smallc) {
+    if (bn == 256) return launch_wgrad<T, 256, true>(tdy, g, dw, st);
+    if (bn == 128) return launch_wgrad<T, 128, true>(tdy, g, dw, st);
+    return launch_wgrad<T, 64, true>(tdy, g, dw, st);
+  }
+  if (bn == 256) return launch_wgrad<T, 256, false>(tdy, g, dw, st);
+  if (bn == 128) return launch_wgrad<T, 128, false>(tdy, g, dw, st);
+  return launch_wgrad<T, 64, false>(tdy, g, dw, st);
+}
+
+}  // namespace
+}  // namespace tc
+}  // namespace simclr
+
+using namespace simclr;
+
+extern "C" {
+
+int simclr_conv2d_fprop_tc(const void* x, const void* wf, void* y, int dtype, int y_dtype, int64_t N, int64_t H,
+                           int64_t W, int64_t Cs, int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream) {
+  SIMCLR_CHECK_ARG(x && wf && y, "conv2d_fprop_tc: null pointer");
+  SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cs > 0 && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
+                   "conv2d_fprop_tc: bad geometry");
+  const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  return tc::run_igemm(0, x, wf, y, dtype, y_dtype, N, H, W, Cs, Ho, Wo, Cout, R, S, stride, (cudaStream_t)stream,
+                       "conv2d_fprop_tc");
+}
+
+int simclr_conv2d_dgrad_tc(const void* dy, const void* wd, void* dx, int dtype, int dx_dtype, int64_t N, int64_t H,
+                           int64_t W, int64_t Cin, int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream) {
+  SIMCLR_CHECK_ARG(dy && wd && dx, "conv2d_dgrad_tc: null pointer");
+  SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
+                   "conv2d_dgrad_tc: bad geometry");
+  const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  // gathered tensor is dY [N][Ho][Wo][Cout]; GEMM rows are the pixels of dX
+  return tc::run_igemm(1, dy, wd, dx, dtype, dx_dtype, N, Ho, Wo, Cout, H, W, Cin, R, S, stride, (cudaStream_t)stream,
+                       "conv2d_dgrad_tc");
+}
+
+int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, int64_t N, int64_t H, int64_t W,
+                           int64_t Cs, int64_t Cin, int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream) {
+  using namespace simclr::tc;
+  SIMCLR_CHECK_ARG(x && dy && dw, "conv2d_wgrad_tc: null pointer");
+  SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cs >= Cin && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
+                   "conv2d_wgrad_tc: bad geometry");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int es = dtype == SIMCLR_BF16 ? 2 : 4;
+  const int ATOM_E = 128 / es, CH = 16 / es;
+  const bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);
+  if (!(Cs % CH == 0 || smallc)) { set_error("conv2d_wgrad_tc: stored channels (%lld) must be a multiple of %d", (long long)Cs, CH); return SIMCLR_ERR_UNSUPPORTED; }
+  if ((Cout * es) % 16 != 0) { set_error("conv2d_wgrad_tc: Cout*elt must be a multiple of 16 bytes"); return SIMCLR_ERR_UNSUPPORTED; }
+  SIMCLR_CHECK_ARG(aligned16(x) && aligned16(dy), "conv2d_wgrad_tc: operands must be 16-byte aligned");
+  const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int64_t M = N * Ho * Wo;
+  if (M >= (1ll << 31)) { set_error("conv2d_wgrad_tc: M too large"); return SIMCLR_ERR_UNSUPPORTED; }
+  const int pxs = dtype == SIMCLR_BF16 ? 64 : 32;
+  const int bn = pick_bn(Cout);
+  Geom g;
+  g.src = x; g.out = nullptr; g.mode = 0;
+  g.H = (int)H; g.W = (int)W; g.C = (int)Cs; g.R = (int)R; g.S = (int)S; g.RS = (int)(R * S);
+  g.stride = (int)stride; g.pad_h = (int)((R - 1) / 2); g.pad_w = (int)((S - 1) / 2);
+  g.dPQ = FastDiv((uint32_t)(Ho * Wo)); g.dQ = FastDiv((uint32_t)Wo); g.dC = FastDiv((uint32_t)Cs); g.dS = FastDiv((uint32_t)S);
+  g.M = M; g.n_out = (int)Cout; g.ldc = (int)Cout;
+  g.num_kb = (int)((M + pxs - 1) / pxs);
+  g.tiles_m = (int)((R * S * Cs + 127) / 128); g.tiles_n = (int)((Cout + bn - 1) / bn);
+  g.Cin = (int)Cin; g.Cout = (int)Cout;
+  const int tiles = g.tiles_m * g.tiles_n;
+  int splits = (2 * num_sms() + tiles - 1) / tiles;
+  const int max_splits = g.num_kb / 8 > 0 ? g.num_kb / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  g.kb_per_split = (g.num_kb + splits - 1) / splits;
+  g.splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;
+  CUtensorMap tdy;
+  int rc = make_tmap_2d(&tdy, dy, es, (uint64_t)M, (uint64_t)Cout, (uint64_t)Cout * es, (uint32_t)pxs, (uint32_t)ATOM_E);
+  if (rc) return rc;
+  SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(R * S * Cin * Cout) * sizeof(float), st));
+  if (dtype == SIMCLR_BF16) return dispatch_wgrad<__nv_bfloat16>(bn, smallc, tdy, g, dw, st);
+  if (dtype == SIMCLR_F32) return dispatch_wgrad<float>(bn, false, tdy, g, dw, st);
+  set_error("conv2d_wgrad_tc: unknown dtype %d", dtype);
+  return SIMCLR_ERR_INVALID_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+"""Device-side plumbing shared by the layers: variables in flat fp32 buffers,
+the replica context (one process per GPU, torch.distributed over NCCL), and thin
+wrappers that hand `data_ptr()`s to the C-ABI.  PyTorch here is memory owner and
+stream/collective plumbing only -- every FLOP of the step runs in
+libsimclr_b200.so.
+"""
+import math
+import os
+
+import torch
+import torch.distributed as dist
+
+from ._lib import lib, DTYPE_CODE, F32, BF16, SimclrError, stream_ptr
+from .flags_def import FLAGS
+
+BATCH_NORM_EPSILON = 1e-5  # tf2/resnet.py:28
+
+
+class Variable:
+    """A trainable tensor (name follows the Keras naming the reference's LARS
+    filters rely on, tf2/model.py:40-42) or a moving statistic."""
+
+    def __init__(self, name, shape, init, trainable=True):
+        self.name = name
+        self.shape = tuple(shape)
+        self.init = init
+        self.trainable = trainable
+        self.value = None      # fp32 view into the flat parameter buffer
+        self.grad = None       # fp32 view into the flat gradient buffer
+
+    @property
+    def numel(self):
+        return math.prod(self.shape)
+
+    def __repr__(self):
+        return 'Variable(%s, %s)' % (self.name, self.shape)
+
+
+class _Namer:
+    def __init__(self):
+        self.counts = {}
+
+    def __call__(self, base):
+        n = self.counts.get(base, 0)
+        self.counts[base] = n + 1
+        return base if n == 0 else '%s_%d' % (base, n)
+
+
+class VarStore:
+    """Creation-ordered variables; `materialize` lays them out in flat buffers so
+    the gradient all-reduce and the LARS tables see contiguous memory."""
+
+    ALIGN = 64   # elements (256 B): float4 / TMA friendly offsets
+
+    def __init__(self):
+        self.namer = _Namer()
+        self.trainable = []
+        self.moving = []
+        self.flat_value = self.flat_grad = self.flat_moving = None
+
+    def add(self, name, shape, init, trainable=True):
+        v = Variable(name, shape, init, trainable)
+        (self.trainable if trainable else self.moving).append(v)
+        return v
+
+    def _layout(self, vs):
+        off, offs = 0, []
+        for v in vs:
+            offs.append(off)
+            off += (v.numel + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        return offs, off
+
+    def materialize(self, device, seed=0):
+        offs, total = self._layout(self.trainable)
+        self.flat_value = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
+        for v, o in zip(self.trainable, offs):
+            v.value = self.flat_value[o:o + v.numel].view(v.shape)
+            v.grad = self.flat_grad[o:o + v.numel].view(v.shape)
+        offs, total = self._layout(self.moving)
+        self.flat_moving = torch.zeros(total, dtype=torch.float32, device=device)
+        for v, o in zip(self.moving, offs):
+            v.value = self.flat_moving[o:o + v.numel].view(v.shape)
+        self.initialize(seed)
+
+    def initialize(self, seed=0):
+        """Reference initialisers, generated on the host so every
+        rank (and the oracle, given the same tensors) starts identical."""
+        g = torch.Generator().manual_seed(seed)
+        for v in self.trainable + self.moving:
+            v.value.copy_(_init_tensor(v.shape, v.init, g))
+
+    def load(self, tensors):
+        """Copies name -> tensor (oracle / checkpoint layout) into the variables."""
+        byname = {v.name: v for v in self.trainable + self.moving}
+        for k, t in tensors.items():
+            if k not in byname:
+                raise KeyError('unknown variable %r' % k)
+            if tuple(t.shape) != byname[k].shape:
+                raise ValueError('shape mismatch for %s: %s vs %s' % (k, tuple(t.shape), byname[k].shape))
+            byname[k].value.copy_(t.to(torch.float32))
+
+
+def _init_tensor(shape, init, g):
+    if init == 'zeros':
+        return torch.zeros(shape)
+    if init == 'ones':
+        return torch.ones(shape)
+    if init == 'variance_scaling':      # tf2/resnet.py:202
+        fan_in = math.prod(shape[:-1])
+        std = math.sqrt(1.0 / fan_in) / 0.87962566103423978
+        t = torch.empty(shape, dtype=torch.float64)
+        torch.nn.init.trunc_normal_(t, 0.0, 1.0, -2.0, 2.0, generator=g)
+        return (t * std).float()
+    if init == 'normal_0.01':           # tf2/model.py:145
+        return (torch.randn(shape, dtype=torch.float64, generator=g) * 0.01).float()
+    raise ValueError(init)
+
+
+class ReplicaContext:
+    """Stand-in for `tf.distribute` replica context / strategy: one process per GPU."""
+
+    def __init__(self, group=None):
+        if dist.is_available() and dist.is_initialized():
+            self.num_replicas_in_sync = dist.get_world_size(group)
+            self.replica_id = dist.get_rank(group)
+        else:
+            self.num_replicas_in_sync = 1
+            self.replica_id = 0
+        self.group = group
+
+    def all_reduce_sum(self, t):
+        if self.num_replicas_in_sync > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_gather(self, t):
+        """[...] -> [R, ...] (rank-major)."""
+        R = self.num_replicas_in_sync
+        if R == 1:
+            return t.unsqueeze(0)
+        t = t.contiguous()
+        out = torch.empty((R * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)      # concatenation along dim 0
+        return out.view((R,) + tuple(t.shape))
+
+
+class Engine:
+    """Per-process execution context: activation dtype, conv engine, replica context."""
+
+    def __init__(self, device=None, precision=None, conv_engine=None, ctx=None):
+        if not torch.cuda.is_available():
+            raise SimclrError('simclr_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        lib.load()
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        precision = precision or FLAGS.b200_precision
+        self.act_dtype = torch.bfloat16 if precision == 'bf16' else torch.float32
+        self.conv_engine = conv_engine or FLAGS.b200_conv_engine
+        self.ctx = ctx or ReplicaContext()
+        self.launches = 0          # kernel launches issued through the C-ABI (gpu_launches claim)
+
+    # -- helpers ---------------------------------------------------------
+    def code(self, dtype):
+        return DTYPE_CODE[dtype]
+
+    def empty(self, shape, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.act_dtype, device=self.device)
+
+    def zeros(self, shape, dtype=None):
+        return torch.zeros(shape, dtype=dtype or self.act_dtype, device=self.device)
+
+    @property
+    def sync_bn(self):
+        return bool(FLAGS.global_bn) and self.ctx.num_replicas_in_sync > 1
+
+
+_ENGINE = None
+
+
+def get_engine():
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine()
+    return _ENGINE
+
+
+def set_engine(e):
+    global _ENGINE
+    _ENGINE = e
+    return e

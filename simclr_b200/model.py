@@ -1,0 +1,254 @@
+"""Model, heads, LR schedule and optimizer factory of the reference
+(`tf2/model.py`) on the B200 engine.  Same class / function names, constructor
+arguments and error behaviour; variables are laid out in flat buffers and the
+backward pass is an explicit schedule (`Model.backward`).
+"""
+import math
+
+import torch
+
+from ._lib import lib, stream_ptr
+from .engine import VarStore, get_engine
+from .flags_def import FLAGS
+from . import resnet
+from . import lars_optimizer
+from . import data_util
+
+
+def build_optimizer(learning_rate):
+    """tf2/model.py:29-44."""
+    if FLAGS.optimizer == 'lars':
+        return lars_optimizer.LARSOptimizer(
+            learning_rate,
+            momentum=FLAGS.momentum,
+            weight_decay=FLAGS.weight_decay,
+            exclude_from_weight_decay=['batch_normalization', 'bias', 'head_supervised'])
+    elif FLAGS.optimizer in ('momentum', 'adam'):
+        raise NotImplementedError(
+            "optimizer=%r: only 'lars' (the pretraining optimizer) is on the B200 path" % FLAGS.optimizer)
+    else:
+        raise ValueError('Unknown optimizer {}'.format(FLAGS.optimizer))
+
+
+def add_weight_decay(model, adjust_per_optimizer=True):
+    """tf2/model.py:47-69.  Returns the loss term as a device scalar tensor (or 0)."""
+    e = get_engine()
+    if adjust_per_optimizer and 'lars' in FLAGS.optimizer:
+        vs = [v for v in model.trainable_variables if 'head_supervised' in v.name and 'bias' not in v.name]
+    else:
+        vs = [v for v in model.trainable_weights if 'batch_normalization' not in v.name]
+    if not vs:
+        return 0
+    total = e.zeros((1,), torch.float32)
+    for v in vs:
+        out = e.empty((257,), torch.float32)
+        lib.l2_loss(v.value, v.numel, out, stream_ptr())
+        total += out[:1]
+    return FLAGS.weight_decay * total[0]
+
+
+def get_train_steps(num_examples):
+    """tf2/model.py:72-75."""
+    return FLAGS.train_steps or (num_examples * FLAGS.train_epochs // FLAGS.train_batch_size + 1)
+
+
+class WarmUpAndCosineDecay:
+    """tf2/model.py:78-116 (host scalar; evaluated at the pre-increment iteration)."""
+
+    def __init__(self, base_learning_rate, num_examples, name=None):
+        self.base_learning_rate = base_learning_rate
+        self.num_examples = num_examples
+        self._name = name
+
+    def __call__(self, step):
+        step = int(step)
+        warmup_steps = int(round(FLAGS.warmup_epochs * self.num_examples // FLAGS.train_batch_size))
+        if FLAGS.learning_rate_scaling == 'linear':
+            scaled_lr = self.base_learning_rate * FLAGS.train_batch_size / 256.
+        elif FLAGS.learning_rate_scaling == 'sqrt':
+            scaled_lr = self.base_learning_rate * math.sqrt(FLAGS.train_batch_size)
+        else:
+            raise ValueError('Unknown learning rate scaling {}'.format(FLAGS.learning_rate_scaling))
+        learning_rate = step / float(warmup_steps) * scaled_lr if warmup_steps else scaled_lr
+        total_steps = get_train_steps(self.num_examples)
+        decay_steps = total_steps - warmup_steps
+        if step < warmup_steps:
+            return learning_rate
+        s = min(step - warmup_steps, decay_steps)
+        return scaled_lr * 0.5 * (1.0 + math.cos(math.pi * s / decay_steps))   # CosineDecay, alpha=0
+
+    def get_config(self):
+        return {'base_learning_rate': self.base_learning_rate, 'num_examples': self.num_examples}
+
+
+class LinearLayer:
+    """tf2/model.py:119-154: Dense (a 1x1 'conv' on [rows,1,1,Cin]) + optional BN."""
+
+    def __init__(self, vs, scope, cin, num_classes, use_bias=True, use_bn=False, name='linear_layer',
+                 need_dgrad=True):
+        self.num_classes = num_classes
+        self.use_bias = use_bias
+        self.use_bn = use_bn
+        self._name = name
+        scope = scope + '/' + name
+        dname = vs.namer('dense')
+        self.kernel = vs.add('%s/%s/kernel:0' % (scope, dname), (cin, num_classes), 'normal_0.01')
+        self.bias = None
+        if use_bias and not use_bn:
+            self.bias = vs.add('%s/%s/bias:0' % (scope, dname), (num_classes,), 'zeros')
+        self.op = resnet.ConvOp(self.kernel, 1, 1, cin, num_classes, 1, need_dgrad=need_dgrad)
+        if use_bn:
+            self.bn_relu = resnet.BatchNormRelu(vs, scope, num_classes, relu=False, center=use_bias)
+        self.cin = cin
+
+    def __call__(self, inputs, training, relu=False, out_dtype=None):
+        assert inputs.dim() == 2, inputs.shape
+        e = get_engine()
+        rows = inputs.shape[0]
+        y_dtype = out_dtype if (out_dtype is not None and not self.use_bn) else (
+            torch.float32 if out_dtype == torch.float32 else None)
+        y = self.op.forward(inputs.view(rows, 1, 1, self.cin), training, out_dtype=y_dtype).view(rows, self.num_classes)
+        if self.bias is not None:
+            assert y.dtype == torch.float32
+            lib.bias_add(y, self.bias.value, rows, self.num_classes, stream_ptr())
+        if self.use_bn:
+            y = self.bn_relu(y, training, relu=relu, out_dtype=out_dtype)
+        return y
+
+    def backward(self, d, need_dx=True):
+        e = get_engine()
+        if self.use_bn:
+            d = self.bn_relu.backward(d, dy_dtype=e.act_dtype)
+        rows = d.shape[0]
+        if self.bias is not None:
+            lib.bias_grad(d, self.bias.grad, rows, self.num_classes, stream_ptr())
+        if d.dtype != e.act_dtype:
+            dc = e.empty(d.shape)
+            lib.cast(d, e.code(d.dtype), dc, e.code(dc.dtype), d.numel(), stream_ptr())
+            d = dc
+        dx = self.op.backward(d.view(rows, 1, 1, self.num_classes), need_dx)
+        return None if dx is None else dx.view(rows, self.cin)
+
+
+class ProjectionHead:
+    """tf2/model.py:157-213."""
+
+    def __init__(self, vs=None, cin=None, **kwargs):
+        self.linear_layers = []
+        scope = 'projection_head'
+        if FLAGS.proj_head_mode == 'none':
+            pass
+        elif FLAGS.proj_head_mode == 'linear':
+            self.linear_layers = [LinearLayer(vs, scope, cin, FLAGS.proj_out_dim, use_bias=False, use_bn=True,
+                                              name='l_0')]
+        elif FLAGS.proj_head_mode == 'nonlinear':
+            for j in range(FLAGS.num_proj_layers):
+                if j != FLAGS.num_proj_layers - 1:
+                    # for the middle layers, use bias and relu for the output.
+                    self.linear_layers.append(LinearLayer(vs, scope, cin, cin, use_bias=True, use_bn=True,
+                                                          name='nl_%d' % j))
+                else:
+                    # for the final layer, neither bias nor relu is used.
+                    self.linear_layers.append(LinearLayer(vs, scope, cin, FLAGS.proj_out_dim, use_bias=False,
+                                                          use_bn=True, name='nl_%d' % j))
+        else:
+            raise ValueError('Unknown head projection mode {}'.format(FLAGS.proj_head_mode))
+
+    def __call__(self, inputs, training):
+        if FLAGS.proj_head_mode == 'none':
+            return inputs  # the reference's caller then fails to unpack
+        if FLAGS.proj_head_mode == 'linear':
+            raise ValueError("proj_head_mode='linear' returns None in the reference (tf2/model.py:196-199)")
+        hiddens_list = [inputs]
+        n = FLAGS.num_proj_layers
+        for j in range(n):
+            last = j == n - 1
+            # ReLU of the middle layers (tf2/model.py:203-205) is fused into the BN apply;
+            # the final layer's output is fp32 for the loss.
+            hiddens = self.linear_layers[j](hiddens_list[-1], training, relu=not last,
+                                            out_dtype=torch.float32 if last else None)
+            hiddens_list.append(hiddens)
+        return hiddens_list[-1], hiddens_list[FLAGS.ft_proj_selector]
+
+    def backward(self, d_proj_out):
+        d = d_proj_out
+        for layer in reversed(self.linear_layers):
+            d = layer.backward(d)
+        return d
+
+
+class SupervisedHead:
+    """tf2/model.py:216-225."""
+
+    def __init__(self, num_classes, vs=None, cin=None, name='head_supervised', **kwargs):
+        self.linear_layer = LinearLayer(vs, name, cin, num_classes, need_dgrad=False)
+
+    def __call__(self, inputs, training):
+        return self.linear_layer(inputs, training, out_dtype=torch.float32)
+
+    def backward(self, d_logits):
+        self.linear_layer.backward(d_logits, need_dx=False)
+
+
+class Model:
+    """Resnet model with projection or supervised layer (tf2/model.py:228-280)."""
+
+    def __init__(self, num_classes, seed=0, **kwargs):
+        e = get_engine()
+        self.vs = VarStore()
+        self.resnet_model = resnet.resnet(
+            self.vs, resnet_depth=FLAGS.resnet_depth, width_multiplier=FLAGS.width_multiplier,
+            cifar_stem=FLAGS.image_size <= 32)
+        self._projection_head = ProjectionHead(self.vs, self.resnet_model.cout)
+        if FLAGS.train_mode == 'finetune' or FLAGS.lineareval_while_pretraining:
+            self.supervised_head = SupervisedHead(num_classes, self.vs, self.resnet_model.cout)
+        self.vs.materialize(e.device, seed)
+        self._blur_draws = None
+
+    @property
+    def trainable_variables(self):
+        return self.vs.trainable
+
+    trainable_weights = trainable_variables
+
+    @property
+    def variables(self):
+        return self.vs.trainable + self.vs.moving
+
+    def set_blur_draws(self, sigma, selector):
+        """Injects the `tf.random` draws of `batch_random_blur` (tf2/data_util.py:407,425):
+        sigma [T] floats, selector [T][B] in {0,1}.  None -> drawn on device."""
+        self._blur_draws = (sigma, selector)
+
+    def __call__(self, inputs, training, endpoints=None):
+        e = get_engine()
+        if training and FLAGS.train_mode == 'pretrain':
+            if FLAGS.fine_tune_after_block > -1:
+                raise ValueError('Does not support layer freezing during pretraining,'
+                                 'should set fine_tune_after_block<=-1 for safety.')
+        if inputs.dim() != 4 or inputs.shape[3] is None:
+            raise ValueError('The input channels dimension must be statically known '
+                             f'(got input shape {tuple(inputs.shape)})')
+        if FLAGS.train_mode == 'finetune':
+            raise NotImplementedError('train_mode=finetune is not on the B200 path yet')
+        B, H, W, C6 = inputs.shape
+        num_transforms = C6 // 3
+        use_blur = bool(FLAGS.use_blur and training and FLAGS.train_mode == 'pretrain')
+        # split channels into views, batch_random_blur, concat on batch (view-major),
+        # cast to the activation dtype and pad 3 -> 4 channels: one fused prep pass.
+        features = data_util.prepare_views(inputs, num_transforms, use_blur, FLAGS.image_size,
+                                           draws=self._blur_draws)
+        hiddens = self.resnet_model(features, training=training, endpoints=endpoints)
+        projection_head_outputs, supervised_head_inputs = self._projection_head(hiddens, training)
+        if FLAGS.train_mode == 'pretrain' and FLAGS.lineareval_while_pretraining:
+            # stop_gradient: nothing flows back from the supervised head (tf2/model.py:272-278)
+            supervised_head_outputs = self.supervised_head(supervised_head_inputs, training)
+            return projection_head_outputs, supervised_head_outputs
+        return projection_head_outputs, None
+
+    def backward(self, d_projection_head_outputs, d_supervised_head_outputs=None):
+        """Explicit `tape.gradient` (tf2/run.py:621): fills `.grad` of every trainable variable."""
+        if d_supervised_head_outputs is not None:
+            self.supervised_head.backward(d_supervised_head_outputs)
+        d_hiddens = self._projection_head.backward(d_projection_head_outputs)
+        self.resnet_model.backward(d_hiddens)

@@ -1,0 +1,369 @@
+"""ResNet of the reference (`tf2/resnet.py`) with an explicit forward/backward
+schedule on the sm_100a kernels -- no framework autograd on the GPU path.
+
+Class names, constructor arguments and the `resnet()` factory mirror
+`tf2/resnet.py:31-78,160-208,314-526,529-747`.  Every layer object has
+`__call__(inputs, training)` (forward, stashes what backward needs) and
+`backward(grad)`.  Activations are NHWC torch tensors in the engine's activation
+dtype; variables are fp32 HWIO / [C] views into flat buffers.
+
+Not yet on the GPU path (raise at construction): SK (`sk_ratio > 0`) and SE
+(`se_ratio > 0`) blocks.
+"""
+import torch
+
+from ._lib import lib, stream_ptr, F32
+from .engine import get_engine, BATCH_NORM_EPSILON
+from .flags_def import FLAGS
+
+
+class BatchNormRelu:  # pylint: disable=missing-docstring
+    """tf2/resnet.py:31-78.  (Sync)BatchNormalization + optional ReLU; the
+    residual add + ReLU of the block tail (tf2/resnet.py:382,487) can be fused in."""
+
+    def __init__(self, vs, scope, channels, relu=True, init_zero=False, center=True, scale=True):
+        self.relu = relu
+        self.C = channels
+        lname = vs.namer('batch_norm_relu')
+        bn = vs.namer('sync_batch_normalization' if FLAGS.global_bn else 'batch_normalization')
+        pre = '%s/%s/%s' % (scope, lname, bn)
+        self.gamma = vs.add(pre + '/gamma:0', (channels,), 'zeros' if init_zero else 'ones') if scale else None
+        self.beta = vs.add(pre + '/beta:0', (channels,), 'zeros') if center else None
+        self.moving_mean = vs.add(pre + '/moving_mean:0', (channels,), 'zeros', trainable=False)
+        self.moving_variance = vs.add(pre + '/moving_variance:0', (channels,), 'ones', trainable=False)
+        self.saved = None
+
+    def __call__(self, inputs, training, residual=None, relu=None, out_dtype=None):
+        e = get_engine()
+        relu = self.relu if relu is None else relu
+        C = self.C
+        y = inputs
+        rows = y.numel() // C
+        st = stream_ptr()
+        stats = e.empty((4, C), torch.float32)     # mean, rstd, scale, shift
+        mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
+        g = None if self.gamma is None else self.gamma.value
+        b = None if self.beta is None else self.beta.value
+        if training:
+            sums = e.empty((2 * C,), torch.float64)
+            lib.bn_stats(y, e.code(y.dtype), rows, C, sums, st)
+            count = float(rows)
+            if e.sync_bn:            # SyncBatchNormalization: all-reduce sum x, sum x^2 (C2)
+                e.ctx.all_reduce_sum(sums)
+                count *= e.ctx.num_replicas_in_sync
+            lib.bn_finalize(sums, count, g, b, BATCH_NORM_EPSILON, float(FLAGS.batch_norm_decay),
+                            self.moving_mean.value, self.moving_variance.value, mean, rstd, scale, shift, C, st)
+        else:
+            r = torch.rsqrt(self.moving_variance.value + BATCH_NORM_EPSILON)
+            sc = r if g is None else g * r
+            mean.copy_(self.moving_mean.value); rstd.copy_(r); scale.copy_(sc)
+            shift.copy_(-self.moving_mean.value * sc if b is None else b - self.moving_mean.value * sc)
+        z = e.empty(y.shape, out_dtype or y.dtype)
+        lib.bn_apply(y, e.code(y.dtype), residual, z, e.code(z.dtype), rows, C, scale, shift, int(relu), st)
+        if training:
+            self.saved = (y, z if relu else None, mean, rstd, rows)
+        return z
+
+    def backward(self, dz, dz2=None, dy_dtype=None):
+        """dz (and dz2) are gradients w.r.t. the layer output; dz is overwritten
+        with (dz + dz2) * relu_mask when either applies.  Returns d(inputs)."""
+        e = get_engine()
+        y, zmask, mean, rstd, rows = self.saved
+        self.saved = None
+        C = self.C
+        st = stream_ptr()
+        sums = e.empty((2 * C,), torch.float64)
+        if zmask is not None:
+            assert zmask.dtype == dz.dtype
+        lib.bn_bwd_reduce(dz, dz2, zmask, e.code(dz.dtype), y, e.code(y.dtype), rows, C, mean, rstd, sums, st)
+        sums_g, count = sums, float(rows)
+        if e.sync_bn:
+            sums_g = sums.clone()
+            e.ctx.all_reduce_sum(sums_g)
+            count *= e.ctx.num_replicas_in_sync
+        dy = e.empty(y.shape, dy_dtype or e.act_dtype)
+        coef = e.empty((3 * C,), torch.float32)
+        lib.bn_bwd_apply(dz, e.code(dz.dtype), y, e.code(y.dtype), dy, e.code(dy.dtype), rows, C, mean, rstd,
+                         None if self.gamma is None else self.gamma.value, sums_g, sums, count,
+                         None if self.gamma is None else self.gamma.grad,
+                         None if self.beta is None else self.beta.grad, coef, st)
+        return dy
+
+
+class ConvOp:
+    """Implicit-GEMM convolution on the tcgen05 engine (or the CUDA-core
+    verification engine).  `kernel` is the fp32 HWIO master; the tcgen05 engine
+    reads K-major packed copies refreshed from the master on every forward."""
+
+    def __init__(self, kernel, R, S, cin, cout, stride, stored_cin=None, need_dgrad=True):
+        self.kernel = kernel
+        self.R, self.S, self.cin, self.cout, self.stride = R, S, cin, cout, stride
+        self.cs = stored_cin or cin
+        self.need_dgrad = need_dgrad
+        self.wf = self.wd = None
+        self.saved_x = None
+
+    def _pack(self, e):
+        es = 2 if e.act_dtype == torch.bfloat16 else 4
+        kbe = 128 // es
+        K = self.R * self.S * self.cs
+        Kp = (K + kbe - 1) // kbe * kbe
+        if self.wf is None or self.wf.dtype != e.act_dtype:
+            self.wf = e.empty((self.cout, Kp))
+            self.wd = e.empty((self.cin, self.R * self.S * self.cout)) if self.need_dgrad else None
+        lib.pack_conv_weight(self.kernel.value, self.wf, self.wd, e.code(e.act_dtype), self.R, self.S, self.cin,
+                             self.cs, self.cout, Kp, stream_ptr())
+
+    def forward(self, x, training, out_dtype=None):
+        e = get_engine()
+        N, H, W, Cs = x.shape
+        assert Cs == self.cs, (x.shape, self.cs)
+        s = self.stride
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        y = e.empty((N, Ho, Wo, self.cout), out_dtype or e.act_dtype)
+        st = stream_ptr()
+        if e.conv_engine == 'tc':
+            self._pack(e)
+            lib.conv2d_fprop_tc(x, self.wf, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs, self.cout,
+                                self.R, self.S, s, st)
+        else:
+            lib.conv2d_fprop_simt(x, self.kernel.value, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs,
+                                  self.cin, self.cout, self.R, self.S, s, st)
+        if training:
+            self.saved_x = x
+        return y
+
+    def backward(self, dy, need_dx=True, dx_dtype=None):
+        e = get_engine()
+        x = self.saved_x
+        self.saved_x = None
+        N, H, W, Cs = x.shape
+        st = stream_ptr()
+        assert dy.dtype == x.dtype, (dy.dtype, x.dtype)
+        tc = e.conv_engine == 'tc'
+        if tc:
+            lib.conv2d_wgrad_tc(x, dy, self.kernel.grad, e.code(x.dtype), N, H, W, Cs, self.cin, self.cout,
+                                self.R, self.S, self.stride, st)
+        else:
+            lib.conv2d_wgrad_simt(x, dy, self.kernel.grad, e.code(x.dtype), N, H, W, Cs, self.cin, self.cout,
+                                  self.R, self.S, self.stride, st)
+        if not (need_dx and self.need_dgrad):
+            return None
+        dx = e.empty((N, H, W, self.cin), dx_dtype or e.act_dtype)
+        if tc:
+            lib.conv2d_dgrad_tc(dy, self.wd, dx, e.code(dy.dtype), e.code(dx.dtype), N, H, W, self.cin, self.cout,
+                                self.R, self.S, self.stride, st)
+        else:
+            lib.conv2d_dgrad_simt(dy, self.kernel.value, dx, e.code(dy.dtype), e.code(dx.dtype), N, H, W,
+                                  self.cin, self.cout, self.R, self.S, self.stride, st)
+        return dx
+
+
+class Conv2dFixedPadding:  # pylint: disable=missing-docstring
+    """tf2/resnet.py:183-208: stride 1 -> 'SAME'; stride > 1 -> FixedPadding +
+    'VALID' (folded into the gather bounds of the kernel), no bias."""
+
+    def __init__(self, vs, scope, cin, filters, kernel_size, strides, stored_cin=None, need_dgrad=True):
+        lname = vs.namer('conv2d_fixed_padding')
+        cname = vs.namer('conv2d')
+        self.kernel = vs.add('%s/%s/%s/kernel:0' % (scope, lname, cname),
+                             (kernel_size, kernel_size, cin, filters), 'variance_scaling')
+        self.op = ConvOp(self.kernel, kernel_size, kernel_size, cin, filters, strides, stored_cin, need_dgrad)
+        self.cout = filters
+
+    def __call__(self, inputs, training):
+        return self.op.forward(inputs, training)
+
+    def backward(self, grad, need_dx=True):
+        return self.op.backward(grad, need_dx)
+
+
+class _Shortcut:
+    """Projection shortcut: Conv1x1(stride) + BN without ReLU (tf2/resnet.py:342-353,415-423)."""
+
+    def __init__(self, vs, scope, cin, filters_out, strides):
+        self.conv = Conv2dFixedPadding(vs, scope, cin, filters_out, 1, strides)
+        self.bn = BatchNormRelu(vs, scope, filters_out, relu=False)
+
+    def __call__(self, x, training):
+        return self.bn(self.conv(x, training), training)
+
+    def backward(self, d):
+        return self.conv.backward(self.bn.backward(d))
+
+
+class ResidualBlock:  # pylint: disable=missing-docstring
+    """tf2/resnet.py:314-382."""
+
+    def __init__(self, vs, scope, cin, filters, strides, use_projection=False):
+        scope = scope + '/' + vs.namer('residual_block')
+        self.shortcut = _Shortcut(vs, scope, cin, filters, strides) if use_projection else None
+        self.c1 = Conv2dFixedPadding(vs, scope, cin, filters, 3, strides)
+        self.b1 = BatchNormRelu(vs, scope, filters)
+        self.c2 = Conv2dFixedPadding(vs, scope, filters, filters, 3, 1)
+        self.b2 = BatchNormRelu(vs, scope, filters, relu=False, init_zero=True)
+        self.cout = filters
+
+    def __call__(self, inputs, training):
+        shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
+        x = self.b1(self.c1(inputs, training), training)
+        x = self.c2(x, training)
+        return self.b2(x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :382
+
+    def backward(self, d_out, d_out2=None):
+        dy = self.b2.backward(d_out, d_out2)      # d_out <- (d_out + d_out2) * [out > 0]
+        d = self.c2.backward(dy)
+        d = self.b1.backward(d)
+        dx_a = self.c1.backward(d)
+        dx_b = d_out if self.shortcut is None else self.shortcut.backward(d_out)
+        return dx_a, dx_b
+
+
+class BottleneckBlock:
+    """tf2/resnet.py:385-487 (DropBlock is dead code in the reference)."""
+
+    def __init__(self, vs, scope, cin, filters, strides, use_projection=False):
+        scope = scope + '/' + vs.namer('bottleneck_block')
+        self.shortcut = _Shortcut(vs, scope, cin, 4 * filters, strides) if use_projection else None
+        self.c1 = Conv2dFixedPadding(vs, scope, cin, filters, 1, 1)
+        self.b1 = BatchNormRelu(vs, scope, filters)
+        self.c2 = Conv2dFixedPadding(vs, scope, filters, filters, 3, strides)
+        self.b2 = BatchNormRelu(vs, scope, filters)
+        self.c3 = Conv2dFixedPadding(vs, scope, filters, 4 * filters, 1, 1)
+        self.b3 = BatchNormRelu(vs, scope, 4 * filters, relu=False, init_zero=True)
+        self.cout = 4 * filters
+
+    def __call__(self, inputs, training):
+        shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
+        x = self.b1(self.c1(inputs, training), training)
+        x = self.b2(self.c2(x, training), training)
+        x = self.c3(x, training)
+        return self.b3(x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :487
+
+    def backward(self, d_out, d_out2=None):
+        dy = self.b3.backward(d_out, d_out2)
+        d = self.c3.backward(dy)
+        d = self.b2.backward(d)
+        d = self.c2.backward(d)
+        d = self.b1.backward(d)
+        dx_a = self.c1.backward(d)
+        dx_b = d_out if self.shortcut is None else self.shortcut.backward(d_out)
+        return dx_a, dx_b
+
+
+class BlockGroup:  # pylint: disable=missing-docstring
+    """tf2/resnet.py:490-526: the first block always has a projection shortcut."""
+
+    def __init__(self, vs, scope, cin, filters, block_fn, blocks, strides, name):
+        self._name = name
+        scope = scope + '/' + name
+        self.layers = [block_fn(vs, scope, cin, filters, strides, use_projection=True)]
+        for _ in range(1, blocks):
+            self.layers.append(block_fn(vs, scope, self.layers[-1].cout, filters, 1))
+        self.cout = self.layers[-1].cout
+
+    def __call__(self, inputs, training):
+        for layer in self.layers:
+            inputs = layer(inputs, training)
+        return inputs
+
+    def backward(self, d, d2=None):
+        for layer in reversed(self.layers):
+            d, d2 = layer.backward(d, d2)
+        return d, d2
+
+
+class Resnet:  # pylint: disable=missing-docstring
+    """tf2/resnet.py:529-699.  Input [N,H,W,4]: 3 image channels + one zero
+    channel so every pixel is 8/16 bytes for the stem's gather."""
+
+    STEM_CS = 4
+
+    def __init__(self, vs, block_fn, layers, width_multiplier, cifar_stem=False):
+        if FLAGS.sk_ratio > 0 or FLAGS.se_ratio > 0:
+            raise NotImplementedError('SK / SE blocks are not on the B200 path yet (sk_ratio/se_ratio must be 0)')
+        scope = 'resnet'
+        wm = width_multiplier
+        self.cifar_stem = cifar_stem
+        if cifar_stem:                                            # :551-564
+            self.stem_conv = Conv2dFixedPadding(vs, scope, 3, 64 * wm, 3, 1, stored_cin=self.STEM_CS, need_dgrad=False)
+        else:                                                     # :593-604
+            self.stem_conv = Conv2dFixedPadding(vs, scope, 3, 64 * wm, 7, 2, stored_cin=self.STEM_CS, need_dgrad=False)
+        self.stem_bn = BatchNormRelu(vs, scope, 64 * wm)
+        self.block_groups = []
+        cin = 64 * wm
+        for i, (f, s) in enumerate(zip([64, 128, 256, 512], [1, 2, 2, 2])):
+            g = BlockGroup(vs, scope, cin, f * wm, block_fn, layers[i], s, 'block_group%d' % (i + 1))
+            self.block_groups.append(g)
+            cin = g.cout
+        self.cout = cin
+        self.saved = None
+
+    def __call__(self, inputs, training, endpoints=None):
+        e = get_engine()
+        st = stream_ptr()
+        x = self.stem_conv(inputs, training)
+        if endpoints is not None:
+            endpoints['initial_conv'] = x
+        x = self.stem_bn(x, training)
+        pool_saved = None
+        if not self.cifar_stem:                                   # MaxPooling2D(3, 2, 'SAME'), :605-611
+            N, H, W, C = x.shape
+            Ho, Wo = (H + 1) // 2, (W + 1) // 2
+            y = e.empty((N, Ho, Wo, C))
+            argmax = e.empty((N, Ho, Wo, C), torch.uint8)
+            lib.maxpool3x3s2_fwd(x, y, argmax, e.code(x.dtype), N, H, W, C, st)
+            pool_saved = (argmax, (N, H, W, C))
+            x = y
+        if endpoints is not None:
+            endpoints['initial_max_pool'] = x
+        for i, g in enumerate(self.block_groups):
+            x = g(x, training)
+            if endpoints is not None:
+                endpoints['block_group%d' % (i + 1)] = x
+        N, H, W, C = x.shape
+        out = e.empty((N, C))
+        lib.global_avgpool_fwd(x, e.code(x.dtype), out, e.code(out.dtype), N, H * W, C, st)   # :693-696
+        if endpoints is not None:
+            endpoints['final_avg_pool'] = out
+        if training:
+            self.saved = (pool_saved, (N, H, W, C))
+        return out
+
+    def backward(self, d_hiddens):
+        e = get_engine()
+        st = stream_ptr()
+        pool_saved, (N, H, W, C) = self.saved
+        self.saved = None
+        d = e.empty((N, H, W, C))
+        lib.global_avgpool_bwd(d_hiddens, e.code(d_hiddens.dtype), d, e.code(d.dtype), N, H * W, C, st)
+        d2 = None
+        for g in reversed(self.block_groups):
+            d, d2 = g.backward(d, d2)
+        if pool_saved is not None:
+            argmax, (N, H, W, C) = pool_saved
+            lib.add_inplace(d, d2, e.code(d.dtype), d.numel(), st)
+            dx = e.empty((N, H, W, C))
+            lib.maxpool3x3s2_bwd(d, argmax, dx, e.code(d.dtype), N, H, W, C, st)
+            d, d2 = dx, None
+        dy = self.stem_bn.backward(d, d2)
+        self.stem_conv.backward(dy, need_dx=False)
+
+
+MODEL_PARAMS = {  # tf2/resnet.py:709-734
+    18: (ResidualBlock, [2, 2, 2, 2]), 34: (ResidualBlock, [3, 4, 6, 3]),
+    50: (BottleneckBlock, [3, 4, 6, 3]), 101: (BottleneckBlock, [3, 4, 23, 3]),
+    152: (BottleneckBlock, [3, 8, 36, 3]), 200: (BottleneckBlock, [3, 24, 36, 3]),
+}
+
+
+def resnet(vs, resnet_depth, width_multiplier, cifar_stem=False, data_format='channels_last',
+           dropblock_keep_probs=None, dropblock_size=None):
+    """tf2/resnet.py:702-747.  Only `channels_last` exists on this path."""
+    if resnet_depth not in MODEL_PARAMS:
+        raise ValueError('Not a valid resnet_depth:', resnet_depth)
+    if data_format != 'channels_last':
+        raise ValueError('only channels_last is supported')
+    del dropblock_keep_probs, dropblock_size      # DropBlock is never enabled by the reference
+    block_fn, layers = MODEL_PARAMS[resnet_depth]
+    return Resnet(vs, block_fn, layers, width_multiplier, cifar_stem=cifar_stem)

@@ -1,0 +1,148 @@
+"""Parity of the tcgen05 / TMA implicit-GEMM engine (fprop, dgrad, wgrad, dense)
+against the oracle's convolution on the same (bf16-rounded) inputs.
+
+bf16 x bf16 products are exact in fp32, so with fp32 outputs the only
+difference from the fp64 reference is fp32 accumulation order: tolerance 2e-4.
+bf16 outputs add one rounding (2^-9 relative): tolerance 8e-3.  tf32 operands
+(fp32 storage, kind::tf32) carry 10 mantissa bits: tolerance 3e-3.
+"""
+import pytest
+import torch
+
+from util import rel_err
+from test_gpu_kernels import conv_reference
+
+pytestmark = pytest.mark.gpu
+
+# N, H, W, Cin, Cs, Cout, k, stride
+CASES = [
+    (2, 16, 16, 64, 64, 256, 1, 1),      # plain GEMM: activations through TMA, BN=256
+    (3, 10, 10, 256, 256, 64, 1, 1),     # M=300 (ragged last tile), BN=64
+    (2, 12, 12, 64, 64, 64, 3, 1),       # gathered 3x3
+    (2, 8, 8, 128, 128, 128, 3, 1),      # BN=128, two K blocks per tap
+    (2, 12, 12, 128, 128, 128, 3, 2),    # strided 3x3 (FixedPadding + VALID)
+    (2, 8, 8, 256, 256, 512, 1, 2),      # strided 1x1 projection shortcut
+    (2, 32, 32, 3, 4, 64, 7, 2),         # stem: 3 channels stored as 4
+    (100, 1, 1, 2048, 2048, 128, 1, 1),  # projection-head dense
+    (64, 1, 1, 512, 512, 1000, 1, 1),    # supervised head: n_out not a tile multiple
+    (1, 5, 7, 64, 64, 64, 3, 1),         # tiny M (35 rows)
+    (4, 28, 28, 128, 128, 512, 1, 1),    # several tiles per CTA? (M=3136 -> 25 tiles x 2)
+    (2, 14, 14, 1024, 1024, 256, 1, 1),  # long K (16 K blocks) through the smem ring
+]
+
+
+def _mk(case, dtype, seed_off=0):
+    N, H, W, Cin, Cs, Cout, k, s = case
+    torch.manual_seed(sum(case) + seed_off)
+    x = torch.randn(N, H, W, Cin).to(dtype)
+    w = (torch.randn(k, k, Cin, Cout) * (1.0 / (k * k * Cin) ** 0.5)).to(dtype)   # weights rounded like the packed copy
+    xs = torch.zeros(N, H, W, Cs, dtype=dtype); xs[..., :Cin] = x
+    return x, w, xs
+
+
+def _pack(w, dtype, k, Cin, Cs, Cout, want_wd=True):
+    from simclr_b200._lib import lib, stream_ptr, DTYPE_CODE
+    es = 2 if dtype == torch.bfloat16 else 4
+    kbe = 128 // es
+    K = k * k * Cs
+    Kp = (K + kbe - 1) // kbe * kbe
+    wf = torch.empty(Cout, Kp, dtype=dtype, device='cuda')
+    wd = torch.empty(Cin, k * k * Cout, dtype=dtype, device='cuda') if (want_wd and Cs == Cin) else None
+    lib.pack_conv_weight(w.float().cuda().contiguous(), wf, wd, DTYPE_CODE[dtype], k, k, Cin, Cs, Cout, Kp, stream_ptr())
+    return wf, wd
+
+
+@pytest.mark.parametrize('out_dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('case', CASES)
+def test_tc_fprop_bf16(case, out_dtype):
+    from simclr_b200._lib import lib, stream_ptr, DTYPE_CODE
+    N, H, W, Cin, Cs, Cout, k, s = case
+    x, w, xs = _mk(case, torch.bfloat16)
+    yo = conv_reference(x.double(), w.double(), k, s)
+    wf, _ = _pack(w, torch.bfloat16, k, Cin, Cs, Cout, want_wd=False)
+    y = torch.full(yo.shape, float('nan'), dtype=out_dtype, device='cuda')
+    lib.conv2d_fprop_tc(xs.cuda(), wf, y, 1, DTYPE_CODE[out_dtype], N, H, W, Cs, Cout, k, k, s, stream_ptr())
+    torch.cuda.synchronize()
+    assert rel_err(y, yo) < (2e-4 if out_dtype == torch.float32 else 8e-3)
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c[3] == c[4]])
+def test_tc_dgrad_bf16(case):
+    from simclr_b200._lib import lib, stream_ptr
+    N, H, W, Cin, Cs, Cout, k, s = case
+    x, w, xs = _mk(case, torch.bfloat16)
+    xo = x.double().requires_grad_(True)
+    yo = conv_reference(xo, w.double(), k, s)
+    dy = torch.randn(yo.shape).to(torch.bfloat16)
+    yo.backward(dy.double())
+    _, wd = _pack(w, torch.bfloat16, k, Cin, Cs, Cout)
+    dx = torch.full((N, H, W, Cin), float('nan'), dtype=torch.float32, device='cuda')
+    lib.conv2d_dgrad_tc(dy.cuda(), wd, dx, 1, 0, N, H, W, Cin, Cout, k, k, s, stream_ptr())
+    torch.cuda.synchronize()
+    assert rel_err(dx, xo.grad) < 2e-4
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_tc_wgrad_bf16(case):
+    from simclr_b200._lib import lib, stream_ptr
+    N, H, W, Cin, Cs, Cout, k, s = case
+    x, w, xs = _mk(case, torch.bfloat16)
+    wo = w.double().requires_grad_(True)
+    yo = conv_reference(x.double(), wo, k, s)
+    dy = torch.randn(yo.shape).to(torch.bfloat16)
+    yo.backward(dy.double())
+    dw = torch.full((k, k, Cin, Cout), float('nan'), dtype=torch.float32, device='cuda')
+    lib.conv2d_wgrad_tc(xs.cuda(), dy.cuda(), dw, 1, N, H, W, Cs, Cin, Cout, k, k, s, stream_ptr())
+    torch.cuda.synchronize()
+    assert rel_err(dw, wo.grad) < 2e-4
+
+
+@pytest.mark.parametrize('case', [CASES[0], CASES[2], CASES[4], CASES[7], CASES[9]])
+def test_tc_tf32(case):
+    """fp32 storage, kind::tf32 operands."""
+    from simclr_b200._lib import lib, stream_ptr
+    N, H, W, Cin, Cs, Cout, k, s = case
+    x, w, xs = _mk(case, torch.float32, 7)
+    xo = x.double().requires_grad_(True); wo = w.double().requires_grad_(True)
+    yo = conv_reference(xo, wo, k, s)
+    dy = torch.randn(yo.shape)
+    yo.backward(dy.double())
+    wf, wd = _pack(w, torch.float32, k, Cin, Cs, Cout)
+    st = stream_ptr()
+    y = torch.full(yo.shape, float('nan'), device='cuda')
+    lib.conv2d_fprop_tc(xs.cuda(), wf, y, 0, 0, N, H, W, Cs, Cout, k, k, s, st)
+    dx = torch.full((N, H, W, Cin), float('nan'), device='cuda')
+    lib.conv2d_dgrad_tc(dy.cuda(), wd, dx, 0, 0, N, H, W, Cin, Cout, k, k, s, st)
+    dw = torch.full((k, k, Cin, Cout), float('nan'), device='cuda')
+    lib.conv2d_wgrad_tc(xs.cuda(), dy.cuda(), dw, 0, N, H, W, Cs, Cin, Cout, k, k, s, st)
+    torch.cuda.synchronize()
+    assert rel_err(y, yo) < 3e-3
+    assert rel_err(dx, xo.grad) < 3e-3
+    assert rel_err(dw, wo.grad) < 3e-3
+
+
+def test_tc_matches_simt_large():
+    """Size-independent check at a BASELINE-sized layer: tcgen05 vs the CUDA-core
+    engine on the same bf16 inputs (R50 stage-2 3x3, 64 views)."""
+    from simclr_b200._lib import lib, stream_ptr
+    N, H, W, C, k, s = 64, 28, 28, 128, 3, 1
+    torch.manual_seed(11)
+    x = torch.randn(N, H, W, C, device='cuda').to(torch.bfloat16)
+    w = (torch.randn(k, k, C, C, device='cuda') * 0.03).to(torch.bfloat16)
+    dy = torch.randn(N, H, W, C, device='cuda').to(torch.bfloat16)
+    wf, wd = _pack(w.cpu(), torch.bfloat16, k, C, C, C)
+    st = stream_ptr()
+    wf32 = w.float().contiguous()
+    y_tc = torch.empty(N, H, W, C, device='cuda'); y_ref = torch.empty_like(y_tc)
+    lib.conv2d_fprop_tc(x, wf, y_tc, 1, 0, N, H, W, C, C, k, k, s, st)
+    lib.conv2d_fprop_simt(x, wf32, y_ref, 1, 0, N, H, W, C, C, C, k, k, s, st)
+    dx_tc = torch.empty(N, H, W, C, device='cuda'); dx_ref = torch.empty_like(dx_tc)
+    lib.conv2d_dgrad_tc(dy, wd, dx_tc, 1, 0, N, H, W, C, C, k, k, s, st)
+    lib.conv2d_dgrad_simt(dy, wf32, dx_ref, 1, 0, N, H, W, C, C, k, k, s, st)
+    dw_tc = torch.empty(k, k, C, C, device='cuda'); dw_ref = torch.empty_like(dw_tc)
+    lib.conv2d_wgrad_tc(x, dy, dw_tc, 1, N, H, W, C, C, C, k, k, s, st)
+    lib.conv2d_wgrad_simt(x, dy, dw_ref, 1, N, H, W, C, C, C, k, k, s, st)
+    torch.cuda.synchronize()
+    assert rel_err(y_tc, y_ref) < 2e-4
+    assert rel_err(dx_tc, dx_ref) < 2e-4
+    assert rel_err(dw_tc, dw_ref) < 5e-4

@@ -1,0 +1,156 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol
+the header declares, the flag surface equals the reference's, the variable
+inventory equals the oracle's, and the multi-replica plumbing (gloo, 2 ranks)."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from simclr_b200 import _lib
+    decls = _lib.parse_header()
+    assert len(decls) >= 30
+    _lib.lib.load()                 # getattr on every declared symbol: raises if one is missing
+    assert _lib.lib.version() >= 100
+    import ctypes
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    for name in decls:
+        assert hasattr(dll, name), name
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from simclr_b200._lib import lib, SimclrError
+    with pytest.raises(SimclrError) as ei:
+        lib.ntxent_normalize(None, 4, 8, 1, None, None, None)
+    assert 'null pointer' in str(ei.value)
+    with pytest.raises(SimclrError):
+        lib.conv2d_fprop_tc(1, 1, 1, 1, 1, 1, 8, 8, 8, 8, 2, 2, 1, None)     # even kernel size
+
+
+def test_flag_surface(flags):
+    F = flags.FLAGS
+    assert len(flags.REFERENCE_FLAG_NAMES) == 48
+    expected = dict(learning_rate=0.3, learning_rate_scaling='linear', warmup_epochs=10, weight_decay=1e-6,
+                    batch_norm_decay=0.9, train_batch_size=512, train_epochs=100, train_steps=0,
+                    optimizer='lars', momentum=0.9, temperature=0.1, hidden_norm=True, proj_head_mode='nonlinear',
+                    proj_out_dim=128, num_proj_layers=3, ft_proj_selector=0, global_bn=True, width_multiplier=1,
+                    resnet_depth=50, sk_ratio=0., se_ratio=0., image_size=224, color_jitter_strength=1.0,
+                    use_blur=True, use_tpu=True, lineareval_while_pretraining=True, fine_tune_after_block=-1,
+                    mode='train', train_mode='pretrain', dataset='imagenet2012', eval_batch_size=256)
+    for k in flags.REFERENCE_FLAG_NAMES:
+        assert k in F, k
+    fresh = {k: F[k].default for k in expected}
+    assert fresh == expected
+    with pytest.raises(Exception):
+        F['learning_rate_scaling'].parse('cubic')        # enum is enforced like in the reference
+
+
+def test_flag_names_match_reference_source():
+    """If the reference tree is mounted (build container only), compare the flag names with it."""
+    ref = '/root/reference/tf2/run.py'
+    if not os.path.exists(ref):
+        pytest.skip('reference not mounted')
+    import re
+    from simclr_b200 import flags_def
+    names = re.findall(r"flags\.DEFINE_\w+\(\s*'(\w+)'", open(ref).read())
+    assert names == flags_def.REFERENCE_FLAG_NAMES
+
+
+@pytest.mark.parametrize('kw', [dict(resnet_depth=18, image_size=64), dict(resnet_depth=50), dict(resnet_depth=50, width_multiplier=2),
+                                dict(resnet_depth=34, image_size=32, global_bn=False)])
+def test_variable_inventory_matches_oracle(flags, kw):
+    from simclr_b200 import resnet, model, engine
+    from oracle import model as OM
+    from util import cfg_from_flags
+    flags.set_flags(**kw)
+    vs = engine.VarStore()
+    net = resnet.resnet(vs, flags.FLAGS.resnet_depth, flags.FLAGS.width_multiplier, cifar_stem=flags.FLAGS.image_size <= 32)
+    model.ProjectionHead(vs, net.cout)
+    model.SupervisedHead(1000, vs, net.cout)
+    om = OM.Model(cfg_from_flags(flags.FLAGS), 1000)
+    assert [(v.name, v.shape, v.init) for v in vs.trainable] == [(k, s, i) for k, (s, i) in om.vs.trainable.items()]
+    assert [(v.name, v.shape) for v in vs.moving] == [(k, s) for k, (s, i) in om.vs.moving.items()]
+
+
+def test_lr_schedule_matches_oracle(flags):
+    from simclr_b200 import model
+    from oracle import model as OM
+    from util import cfg_from_flags
+    flags.set_flags(train_batch_size=4096, warmup_epochs=10, train_epochs=100)
+    sched = model.WarmUpAndCosineDecay(0.3, 1281167)
+    cfg = cfg_from_flags(flags.FLAGS)
+    for step in [0, 1, 100, 3127, 3128, 20000, 31279, 40000]:
+        assert sched(step) == OM.warmup_and_cosine_decay(cfg, 0.3, 1281167, step)
+    assert model.get_train_steps(1281167) == 1281167 * 100 // 4096 + 1
+
+
+def test_lars_name_filters(flags):
+    from simclr_b200 import lars_optimizer
+    opt = lars_optimizer.LARSOptimizer(0.1, weight_decay=1e-4,
+                                       exclude_from_weight_decay=['batch_normalization', 'bias', 'head_supervised'])
+    assert opt._use_weight_decay('resnet/conv2d/kernel:0') and opt._do_layer_adaptation('resnet/conv2d/kernel:0')
+    for n in ['resnet/batch_norm_relu/sync_batch_normalization/gamma:0', 'head_supervised/linear_layer/dense_3/kernel:0',
+              'head_supervised/linear_layer/dense_3/bias:0']:
+        assert not opt._use_weight_decay(n) and not opt._do_layer_adaptation(n)
+    with pytest.raises(NotImplementedError):
+        lars_optimizer.LARSOptimizer(0.1, use_nesterov=True)
+
+
+def test_model_errors(flags):
+    from simclr_b200 import resnet, engine
+    with pytest.raises(ValueError):
+        resnet.resnet(engine.VarStore(), 51, 1)
+
+
+# ---- multi-replica plumbing over gloo (2 ranks on CPU) ------------------------
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from simclr_b200.engine import ReplicaContext
+    from oracle import objective as O
+    ctx = ReplicaContext()
+    assert ctx.num_replicas_in_sync == world and ctx.replica_id == rank
+    B, D = 6, 16
+    g = torch.Generator().manual_seed(100)
+    hs = [torch.randn(2 * B, D, generator=g, dtype=torch.float64) for _ in range(world)]
+    z = O.l2_normalize(hs[rank])
+    z_all = ctx.all_gather(z)                                   # [R][2B][D] rank-major
+    assert z_all.shape == (world, 2 * B, D)
+    for r in range(world):
+        assert torch.equal(z_all[r], O.l2_normalize(hs[r]))
+    # sharded loss from the gathered tensor == the oracle's replica simulation
+    h1 = z_all[:, :B].reshape(world * B, D); h2 = z_all[:, B:].reshape(world * B, D)
+    st = O.SimStrategy(world, rank, list(z_all[:, :B]), list(z_all[:, B:]))
+    loss, _, labels = O.add_contrastive_loss(z, False, 0.1, st)
+    ref = O.contrastive_loss_replicas(hs, True, 0.1)[rank]
+    assert abs(loss.item() - ref[0].item()) < 1e-12
+    assert torch.equal(labels, ref[2])
+    t = torch.full((4,), float(rank + 1), dtype=torch.float64)
+    ctx.all_reduce_sum(t)
+    assert torch.equal(t, torch.full((4,), float(sum(range(1, world + 1))), dtype=torch.float64))
+    dist.barrier()
+    dist.destroy_process_group()
+    out.put((rank, 'ok'))
+
+
+def test_replica_context_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(2))
+    assert got == [(0, 'ok'), (1, 'ok')]
