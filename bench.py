@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the SimCLR pretrain step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation
+    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference step
+
+N=1 workload: BASELINE.json configs[1] (ResNet-50 1x, batch 512 per GPU,
+224x224 synthetic, proj_dim 128, temperature 0.1, LARS, blur + linear-eval head
+on, SyncBN flag on).  Under torchrun (N>1) every rank keeps 512 samples (weak
+scaling; N=8 is configs[2], global batch 4096).  A "step" is one complete
+`single_step` (tf2/run.py:557-622): forward, NT-Xent, backward, gradient
+all-reduce, LARS.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMAGE = {(50, 1, 224): 48.574, (18, 1, 64): 1.751, (50, 2, 224): 192.406}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=512, help='samples per GPU')
+    ap.add_argument('--resnet_depth', type=int, default=50)
+    ap.add_argument('--width_multiplier', type=int, default=1)
+    ap.add_argument('--image_size', type=int, default=224)
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no_graph', action='store_true')
+    ap.add_argument('--no_cpu_baseline', action='store_true')
+    ap.add_argument('--cpu_batch', type=int, default=16)
+    ap.add_argument('--cpu_steps', type=int, default=2)
+    return ap.parse_args()
+
+
+def workload_string(args, world):
+    return ('ResNet-%d %dx, batch %d per GPU (global %d), %dx%d synthetic, proj_dim 128, temperature 0.1, LARS, '
+            'blur on, lineareval head on, global_bn on' % (args.resnet_depth, args.width_multiplier, args.batch,
+                                                           args.batch * world, args.image_size, args.image_size))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d['bf16_tflops_sustained'], hbm=d['hbm_gbs'], which='measured (sustained bf16, MEASURED_PEAKS.json)')
+    return dict(tflops=1400.0, hbm=6650.0, which='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(',')]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': float(self.samples[0][1]),
+                'power_w_max': max(float(s[2]) for s in self.samples), 'samples': len(self.samples), 'reasons': reasons}
+
+
+def oracle_step_time(args, batch, steps, warmup=1):
+    """Times the CPU restatement of the reference step (oracle/) on the host cores."""
+    import torch
+    from oracle.config import default_cfg
+    from oracle import model as OM, step as OS
+    import collections
+    torch.set_num_threads(os.cpu_count())
+    cfg = default_cfg(resnet_depth=args.resnet_depth, width_multiplier=args.width_multiplier,
+                      image_size=args.image_size, train_batch_size=batch)
+    m = OM.Model(cfg, 1000)
+    P, S = m.init(0)
+    V = collections.OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    g = torch.Generator().manual_seed(1234)
+    f = torch.rand(batch, args.image_size, args.image_size, 6, generator=g)
+    lab = torch.nn.functional.one_hot(torch.randint(0, 1000, (batch,), generator=g), 1000).float()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        P, S, V, info = OS.single_step(m, P, S, V, [f], [lab], 0.1)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), float(info['loss'])
+
+
+def cpu_model_name():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return 'unknown'
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    workload = workload_string(args, max(1, args.gpus))
+    sec, loss = oracle_step_time(args, args.cpu_batch, max(1, args.steps), max(1, min(args.warmup, 1)))
+    ips = args.cpu_batch / sec
+    line = {
+        'impl': 'reference', 'metric': 'images/sec pretrain step', 'value': ips, 'unit': 'images/s', 'n_gpus': 0,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload, 'sample': 'batch %d per step (CPU throughput is ~batch independent)' % args.cpu_batch},
+        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
+                         'sample': '%d steps of batch %d on %s; oracle restatement of tf2/run.py single_step '
+                                   '(TensorFlow is not installable here)' % (args.steps, args.cpu_batch, cpu_model_name())},
+        'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'loss': loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from simclr_b200 import engine, run, flags_def
+    from simclr_b200._lib import lib
+
+    rank = run.init_distributed()
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    B, S = args.batch, args.image_size
+    flags_def.set_flags(resnet_depth=args.resnet_depth, width_multiplier=args.width_multiplier, image_size=S,
+                        train_batch_size=B * world, temperature=0.1, proj_out_dim=128, optimizer='lars',
+                        use_tpu=False, b200_precision=args.precision, b200_conv_engine='tc')
+    eng = engine.set_engine(engine.Engine(precision=args.precision, conv_engine='tc'))
+    trainer = run.Trainer(num_classes=1000, num_examples=1281167, seed=0)
+    features, labels = run.synthetic_batch(B, S, 1000, eng.device, 1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- capture -------------------------------------------------------------
+    use_graph = not args.no_graph
+    launches0 = lib.launch_count
+    if use_graph:
+        trainer.capture(features, labels, warmup=1)
+        launches_per_step = None
+    step_fn = trainer.replay if use_graph else (lambda: trainer.single_step(features, labels))
+    if use_graph:
+        # launches recorded during the capture pass == launches per replay
+        c0 = lib.launch_count
+        trainer2_count = (c0 - launches0) // 2      # warm-up step + capture pass
+        launches_per_step = trainer2_count
+    else:
+        c0 = lib.launch_count
+        step_fn()
+        launches_per_step = lib.launch_count - c0
+
+    for _ in range(max(args.warmup, 3)):
+        step_fn()
+    barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM -----------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step_fn()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(2)
+    t = torch.tensor([ms], device=eng.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    ips = B * world * args.steps / (ms / 1e3)
+    loss_val = float(loss)
+
+    # ---- e2e: host buffers, H2D inside the timed region, D2H of the loss ------
+    host_f = [torch.rand(B, S, S, 6).pin_memory() for _ in range(2)]
+    host_l = [labels.cpu().pin_memory() for _ in range(2)]
+    loss_host = torch.zeros(1).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    dev_f = [torch.empty_like(features), torch.empty_like(features)]
+    dev_l = [torch.empty_like(labels), torch.empty_like(labels)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def h2d(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            dev_f[i % 2].copy_(host_f[i % 2], non_blocking=True)
+            dev_l[i % 2].copy_(host_l[i % 2], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_step(i):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[i % 2])
+        features.copy_(dev_f[i % 2]); labels.copy_(dev_l[i % 2])      # into the graph's static inputs
+        consumed[i % 2].record(cur)
+        l = step_fn()
+        loss_host.copy_(l.reshape(1), non_blocking=True)
+        return l
+
+    for i in range(2):
+        consumed[i].record(torch.cuda.current_stream())
+    e2e_steps = args.steps
+    h2d(0)
+    for i in range(2):              # warm the copy path
+        h2d(i + 1); e2e_step(i)
+    barrier()
+    ev0.record()
+    base = 2
+    for i in range(e2e_steps):
+        h2d(base + i + 1)           # prefetch next step's inputs while this step computes
+        e2e_step(base + i)
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([e2e_ms], device=eng.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ips = B * world * e2e_steps / (float(t.item()) / 1e3)
+    h2d_bytes = features.numel() * 4 + labels.numel() * 4
+
+    # ---- roofline pass: per-launch CUDA-event timing of the tcgen05 kernels ----
+    roof = None
+    if rank == 0:
+        peaks = measured_peaks()
+        eng.profile = []
+        trainer.single_step(features, labels)
+        torch.cuda.synchronize()
+        by = {}
+        for kind, shape, flops, a, b in eng.profile:
+            d = by.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += flops; d[1] += a.elapsed_time(b) * 1e-3; d[2] += 1
+        eng.profile = None
+        tot_f = sum(v[0] for v in by.values()); tot_t = sum(v[1] for v in by.values())
+        achieved = tot_f / tot_t / 1e12 if tot_t > 0 else 0.0
+        key = (args.resnet_depth, args.width_multiplier, S)
+        step_tflops = (ips / world) * GFLOP_PER_IMAGE[key] / 1e3 if key in GFLOP_PER_IMAGE else None
+        roof = {'bound': 'tensor', 'kernel': 'igemm_kernel/wgrad_kernel (tcgen05 implicit GEMM, %d launches/step)' % sum(v[2] for v in by.values()),
+                'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops'],
+                'traffic': None, 'peak_source': peaks['which'],
+                'conv_share_of_step': tot_t * 1e3 / ms_per_step if not use_graph else None,
+                'conv_kernel_ms': tot_t * 1e3,
+                'by_kind': {k: {'tflops': v[0] / v[1] / 1e12, 'ms': v[1] * 1e3, 'launches': v[2]} for k, v in by.items()},
+                'whole_step_tflops': step_tflops,
+                'whole_step_frac': None if step_tflops is None else step_tflops / peaks['tflops']}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            sec, _ = oracle_step_time(args, args.cpu_batch, args.cpu_steps, 1)
+            cpu = {'value': args.cpu_batch / sec, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
+                   'sample': '%d steps of batch %d (same network, %dx%d) on %s; oracle restatement, not TensorFlow'
+                             % (args.cpu_steps, args.cpu_batch, S, S, cpu_model_name())}
+        except Exception as ex:      # the CPU leg must never take the GPU number down
+            cpu = {'value': None, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
+
+    if rank == 0:
+        line = {
+            'metric': 'images/sec pretrain step', 'value': ips, 'unit': 'images/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'tf32',
+            'data': 'synthetic',
+            'config': {'workload': workload_string(args, world),
+                       'l2': 'inputs larger than L2 (activations are GBs per step)',
+                       'cuda_graph': use_graph, 'parallelism': 'dp%d' % world},
+            'e2e': {'value': e2e_ips, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
+            'gpu_launches': launches_per_step * args.steps,
+            'clocks': sampler.summary() if sampler else None,
+            'roofline': roof, 'cpu_baseline': cpu, 'loss': loss_val,
+        }
+        print(json.dumps(line), flush=True)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

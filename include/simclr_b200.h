@@ -183,7 +183,8 @@ SIMCLR_API int simclr_global_avgpool_bwd(const void* dy, int dy_dtype, void* dx,
 
 /* tcgen05 engine operands: K-major packed copies of the fp32 HWIO master.
  *   wf [Cout][Kp]       k = (r*S+s)*Cs + c,   Kp = round_up(R*S*Cs, 128B/elt)
- *   wd [Cin ][R*S*Cout] k = (r*S+s)*Cout + co (NULL: not needed, e.g. the stem) */
+ *   wd [Cin ][Kdp]      k = (r*S+s)*Cout + co, Kdp = round_up(R*S*Cout, 128B/elt)
+ *                       (NULL: not needed, e.g. the stem) */
 SIMCLR_API int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, int64_t R,
                                        int64_t S, int64_t Cin, int64_t Cs, int64_t Cout, int64_t Kp,
                                        void* stream);

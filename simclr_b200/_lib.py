@@ -67,10 +67,16 @@ def _conv(v, ct):
     return v
 
 
+# kernels launched per C-ABI call (for the `gpu_launches` claim of bench.py)
+_LAUNCHES = {'ntxent_forward': 3, 'ntxent_backward': 2, 'contrast_metrics': 3, 'softmax_xent': 2, 'l2_loss': 2,
+             'lars_apply': 2, 'bn_bwd_apply': 2, 'version': 0, 'last_error': 0, 'ntxent_workspace_bytes': 0}
+
+
 class _Lib:
     def __init__(self):
         self._dll = None
         self._decls = parse_header()
+        self.launch_count = 0
 
     def load(self):
         if self._dll is not None:
@@ -104,11 +110,13 @@ class _Lib:
         fn = getattr(self._dll, full)
         restype, argl = self._decls[full]
         cts = [ct for ct, _ in argl]
+        nlaunch = _LAUNCHES.get(name, 1)
 
         def call(*args):
             if len(args) != len(cts):
                 raise TypeError('%s expects %d arguments, got %d' % (full, len(cts), len(args)))
             r = fn(*[_conv(a, ct) for a, ct in zip(args, cts)])
+            self.launch_count += nlaunch
             if restype is ctypes.c_int and name not in ('version',):
                 if r != 0:
                     raise SimclrError('%s failed with status %d: %s' % (full, r, self._dll.simclr_last_error().decode()))

@@ -112,12 +112,12 @@ __global__ void add_inplace_kernel(T* __restrict__ a, const T* __restrict__ b, i
 }
 
 // fp32 HWIO [R][S][Cin][Cout] -> wf [Cout][Kp] (k=(r*S+s)*Cs+c, zero padded) and
-// wd [Cin][R*S*Cout] (k=(r*S+s)*Cout+co).
+// wd [Cin][Kdp] (k=(r*S+s)*Cout+co, zero padded to the K block).
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int R,
-                                   int S, int Cin, int Cs, int Cout, int Kp) {
+                                   int S, int Cin, int Cs, int Cout, int Kp, int Kdp) {
   const int64_t nf = (int64_t)Cout * Kp;
-  const int64_t nd = wd ? (int64_t)Cin * R * S * Cout : 0;
+  const int64_t nd = wd ? (int64_t)Cin * Kdp : 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (int64_t)gridDim.x * blockDim.x) {
     if (i < nf) {
       const int co = (int)(i / Kp), k = (int)(i % Kp);
@@ -127,10 +127,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
       wf[i] = from_f<T>(v);
     } else {
       const int64_t j = i - nf;
-      const int kd = R * S * Cout;
-      const int ci = (int)(j / kd), k = (int)(j % kd);
+      const int ci = (int)(j / Kdp), k = (int)(j % Kdp);
       const int tap = k / Cout, co = k % Cout;
-      wd[j] = from_f<T>(w[((int64_t)tap * Cin + ci) * Cout + co]);
+      wd[j] = from_f<T>(tap < R * S ? w[((int64_t)tap * Cin + ci) * Cout + co] : 0.f);
     }
   }
 }
@@ -313,10 +312,13 @@ int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, 
   SIMCLR_CHECK_ARG(R > 0 && S > 0 && Cin > 0 && Cs >= Cin && Cout > 0 && Kp >= R * S * Cs, "pack_conv_weight: bad shape");
   SIMCLR_CHECK_ARG(wd == nullptr || Cs == Cin, "pack_conv_weight: dgrad copy needs Cs == Cin");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t total = Cout * Kp + (wd ? Cin * R * S * Cout : 0);
+  const int kbe = dtype == SIMCLR_BF16 ? 64 : 32;
+  const int64_t Kdp = (R * S * Cout + kbe - 1) / kbe * kbe;
+  SIMCLR_CHECK_ARG(Kp % kbe == 0, "pack_conv_weight: Kp must be a multiple of %d", kbe);
+  const int64_t total = Cout * Kp + (wd ? Cin * Kdp : 0);
   const unsigned grid = grid_for(total, 256);
-  if (dtype == SIMCLR_BF16) pack_weight_kernel<bf16><<<grid, 256, 0, st>>>(w_hwio, (bf16*)wf, (bf16*)wd, (int)R, (int)S, (int)Cin, (int)Cs, (int)Cout, (int)Kp);
-  else if (dtype == SIMCLR_F32) pack_weight_kernel<float><<<grid, 256, 0, st>>>(w_hwio, (float*)wf, (float*)wd, (int)R, (int)S, (int)Cin, (int)Cs, (int)Cout, (int)Kp);
+  if (dtype == SIMCLR_BF16) pack_weight_kernel<bf16><<<grid, 256, 0, st>>>(w_hwio, (bf16*)wf, (bf16*)wd, (int)R, (int)S, (int)Cin, (int)Cs, (int)Cout, (int)Kp, (int)Kdp);
+  else if (dtype == SIMCLR_F32) pack_weight_kernel<float><<<grid, 256, 0, st>>>(w_hwio, (float*)wf, (float*)wd, (int)R, (int)S, (int)Cin, (int)Cs, (int)Cout, (int)Kp, (int)Kdp);
   else { set_error("pack_conv_weight: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;

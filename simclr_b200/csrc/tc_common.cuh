@@ -28,9 +28,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 // Spin on a phase parity.  A bounded spin turns a protocol bug into a trap (the
 // launch fails with an error) instead of a hung GPU.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (true) {
     asm volatile(
@@ -43,9 +49,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) break;
-    if (++spins > (1u << 26)) {
-      printf("simclr_b200: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-      __trap();
+    if ((++spins & 0xFF) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {     // 4 s: a protocol bug, not a long kernel
+        printf("simclr_b200: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }

@@ -625,6 +625,12 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cs >= Cin && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
                    "conv2d_wgrad_tc: bad geometry");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SIMCLR_F32) {
+    // 32-bit MN-major operands need the 128B_BASE32B swizzle atom, which this kernel does not
+    // implement; fp32 storage is the verification mode and takes its wgrad from the CUDA-core engine.
+    set_error("conv2d_wgrad_tc: fp32 operands are not supported (use conv2d_wgrad_simt)");
+    return SIMCLR_ERR_UNSUPPORTED;
+  }
   const int es = dtype == SIMCLR_BF16 ? 2 : 4;
   const int ATOM_E = 128 / es, CH = 16 / es;
   const bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);
@@ -657,7 +663,6 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   if (rc) return rc;
   SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(R * S * Cin * Cout) * sizeof(float), st));
   if (dtype == SIMCLR_BF16) return dispatch_wgrad<__nv_bfloat16>(bn, smallc, tdy, g, dw, st);
-  if (dtype == SIMCLR_F32) return dispatch_wgrad<float>(bn, false, tdy, g, dw, st);
   set_error("conv2d_wgrad_tc: unknown dtype %d", dtype);
   return SIMCLR_ERR_INVALID_ARG;
 }

@@ -157,7 +157,7 @@ class Engine:
         self.act_dtype = torch.bfloat16 if precision == 'bf16' else torch.float32
         self.conv_engine = conv_engine or FLAGS.b200_conv_engine
         self.ctx = ctx or ReplicaContext()
-        self.launches = 0          # kernel launches issued through the C-ABI (gpu_launches claim)
+        self.profile = None        # list of per-launch (kind, shape, flops, ev0, ev1) when profiling
 
     # -- helpers ---------------------------------------------------------
     def code(self, dtype):

@@ -110,9 +110,25 @@ class ConvOp:
         Kp = (K + kbe - 1) // kbe * kbe
         if self.wf is None or self.wf.dtype != e.act_dtype:
             self.wf = e.empty((self.cout, Kp))
-            self.wd = e.empty((self.cin, self.R * self.S * self.cout)) if self.need_dgrad else None
+            kd = self.R * self.S * self.cout
+            self.wd = e.empty((self.cin, (kd + kbe - 1) // kbe * kbe)) if self.need_dgrad else None
         lib.pack_conv_weight(self.kernel.value, self.wf, self.wd, e.code(e.act_dtype), self.R, self.S, self.cin,
                              self.cs, self.cout, Kp, stream_ptr())
+
+    def _timed(self, e, kind, x_shape, fn):
+        """Optional per-launch CUDA-event timing (bench.py roofline pass)."""
+        if e.profile is None:
+            return fn()
+        N, H, W, _ = x_shape
+        s = self.stride
+        M = N * ((H - 1) // s + 1) * ((W - 1) // s + 1)
+        flops = 2.0 * M * self.R * self.S * self.cin * self.cout
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        r = fn()
+        ev1.record()
+        e.profile.append((kind, (N, H, W, self.cin, self.cout, self.R, s), flops, ev0, ev1))
+        return r
 
     def forward(self, x, training, out_dtype=None):
         e = get_engine()
@@ -124,8 +140,8 @@ class ConvOp:
         st = stream_ptr()
         if e.conv_engine == 'tc':
             self._pack(e)
-            lib.conv2d_fprop_tc(x, self.wf, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs, self.cout,
-                                self.R, self.S, s, st)
+            self._timed(e, 'fprop', x.shape, lambda: lib.conv2d_fprop_tc(
+                x, self.wf, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs, self.cout, self.R, self.S, s, st))
         else:
             lib.conv2d_fprop_simt(x, self.kernel.value, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs,
                                   self.cin, self.cout, self.R, self.S, s, st)
@@ -141,9 +157,12 @@ class ConvOp:
         st = stream_ptr()
         assert dy.dtype == x.dtype, (dy.dtype, x.dtype)
         tc = e.conv_engine == 'tc'
-        if tc:
-            lib.conv2d_wgrad_tc(x, dy, self.kernel.grad, e.code(x.dtype), N, H, W, Cs, self.cin, self.cout,
-                                self.R, self.S, self.stride, st)
+        # fp32 storage (verification mode): the tcgen05 wgrad kernel is bf16-only (MN-major tf32 needs a
+        # different swizzle atom), so the fp32 wgrad runs on the CUDA-core engine.
+        if tc and x.dtype == torch.bfloat16:
+            self._timed(e, 'wgrad', x.shape, lambda: lib.conv2d_wgrad_tc(
+                x, dy, self.kernel.grad, e.code(x.dtype), N, H, W, Cs, self.cin, self.cout, self.R, self.S,
+                self.stride, st))
         else:
             lib.conv2d_wgrad_simt(x, dy, self.kernel.grad, e.code(x.dtype), N, H, W, Cs, self.cin, self.cout,
                                   self.R, self.S, self.stride, st)
@@ -151,8 +170,9 @@ class ConvOp:
             return None
         dx = e.empty((N, H, W, self.cin), dx_dtype or e.act_dtype)
         if tc:
-            lib.conv2d_dgrad_tc(dy, self.wd, dx, e.code(dy.dtype), e.code(dx.dtype), N, H, W, self.cin, self.cout,
-                                self.R, self.S, self.stride, st)
+            self._timed(e, 'dgrad', x.shape, lambda: lib.conv2d_dgrad_tc(
+                dy, self.wd, dx, e.code(dy.dtype), e.code(dx.dtype), N, H, W, self.cin, self.cout, self.R, self.S,
+                self.stride, st))
         else:
             lib.conv2d_dgrad_simt(dy, self.kernel.value, dx, e.code(dy.dtype), e.code(dx.dtype), N, H, W,
                                   self.cin, self.cout, self.R, self.S, self.stride, st)
