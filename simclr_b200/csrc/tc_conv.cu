@@ -25,7 +25,9 @@ template <int BN> struct Tile {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = PIPE_BYTES / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // double-buffered accumulator (power of 2)
-  static constexpr size_t SMEM_BYTES = 1024 /*align*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 2 * A_STAGE_BYTES;           // two [128 rows][128 B] store staging tiles
+  static constexpr int GATHER_DEPTH = STAGES > 4 ? 4 : STAGES - 1;   // cp.async groups in flight per thread
+  static constexpr size_t SMEM_BYTES = 1024 /*align*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
 };
 
 struct Geom {
@@ -41,6 +43,11 @@ struct Geom {
   int tiles_m, tiles_n;
   // wgrad only
   int Cin, Cout, splits, kb_per_split;
+  // strided-dgrad parity classes: taps from a table, output rows scattered with stride `os`
+  int use_tab, cblocks;
+  int tap_sign;        // +1: source = base + (r, s) (fprop / wgrad / tables); -1: base - (r, s) (stride-1 dgrad)
+  int tab_r[9], tab_s[9], tab_kcol[9];
+  int os, oh0, ow0, OH, OW;
 };
 
 template <typename T> struct Elt;
@@ -52,64 +59,25 @@ template <int STAGES> __device__ __forceinline__ void advance(Pipe& p) {
   if (++p.stage == STAGES) { p.stage = 0; p.phase ^= 1; }
 }
 
-// Address of the source pixel for GEMM-row bases (n, bh, bw) and filter tap (r, s); nullptr if padding.
-template <typename T>
-__device__ __forceinline__ const T* src_pixel(const Geom& g, int n, int bh, int bw, int r, int s) {
-  int h, w;
-  if (g.mode == 0) {
-    h = bh + r; w = bw + s;
-    if ((unsigned)h >= (unsigned)g.H || (unsigned)w >= (unsigned)g.W) return nullptr;
+// Per-K-block tap decode shared by the gather loops: K index -> (tap, channel) -> source offset
+// (dr, ds) relative to the row's base pixel.  Done once per stage per thread; the per-row work is
+// then two adds, two unsigned bound checks and one 64-bit multiply-add.
+struct TapRef { int dr, ds; bool ok; };
+__device__ __forceinline__ TapRef decode_tap(const Geom& g, uint32_t tap) {
+  TapRef t;
+  t.ok = (int)tap < g.RS;
+  if (g.use_tab) {
+    const int ti = t.ok ? (int)tap : 0;
+    t.dr = g.tab_r[ti]; t.ds = g.tab_s[ti];
   } else {
-    const int hh = bh - r, ww = bw - s;
-    if (hh < 0 || ww < 0) return nullptr;
-    if (g.stride == 1) { h = hh; w = ww; }
-    else if (g.stride == 2) { if ((hh | ww) & 1) return nullptr; h = hh >> 1; w = ww >> 1; }
-    else { if (hh % g.stride || ww % g.stride) return nullptr; h = hh / g.stride; w = ww / g.stride; }
-    if (h >= g.H || w >= g.W) return nullptr;
+    uint32_t r, s; g.dS.divmod(tap, r, s);
+    t.dr = g.tap_sign * (int)r; t.ds = g.tap_sign * (int)s;
   }
-  return reinterpret_cast<const T*>(g.src) + ((long long)(n * g.H + h) * g.W + w) * g.C;
+  return t;
 }
 
-__device__ __forceinline__ uint4 ldg16(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint2 ldg8(const void* p) {
-  uint2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-  return v;
-}
 __device__ __forceinline__ void sts16(uint32_t saddr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// 16 bytes of K for one gathered row.  SMALLC (bf16, C == 4): the chunk holds two taps of 4 channels.
-template <typename T, bool SMALLC>
-__device__ __forceinline__ uint4 gather_chunk(const Geom& g, int n, int bh, int bw, uint32_t k0) {
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (n < 0) return v;
-  if (!SMALLC) {
-    uint32_t tap, c; g.dC.divmod(k0, tap, c);
-    if ((int)tap < g.RS) {
-      uint32_t r, s; g.dS.divmod(tap, r, s);
-      const T* p = src_pixel<T>(g, n, bh, bw, (int)r, (int)s);
-      if (p) v = ldg16(p + c);
-    }
-  } else {
-    const uint32_t tap0 = k0 >> 2;     // C == 4
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const uint32_t tap = tap0 + half;
-      if ((int)tap < g.RS) {
-        uint32_t r, s; g.dS.divmod(tap, r, s);
-        const T* p = src_pixel<T>(g, n, bh, bw, (int)r, (int)s);
-        if (p) { const uint2 u = ldg8(p); if (half == 0) { v.x = u.x; v.y = u.y; } else { v.z = u.x; v.w = u.y; } }
-      }
-    }
-  }
-  return v;
 }
 
 template <typename To>
@@ -146,11 +114,13 @@ __device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, c
 
 struct SmemCtl {
   uint64_t* full; uint64_t* empty; uint64_t* tmem_full; uint64_t* tmem_empty; uint32_t* tmem_ptr;
+  uint8_t* epi;     // 2 x [128][128 B] staging tiles for the TMA-store epilogue
 };
 template <int STAGES>
 __device__ __forceinline__ SmemCtl carve(uint8_t* base, int stage_bytes) {
   SmemCtl c;
-  uint64_t* b = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * stage_bytes);
+  c.epi = base + (size_t)STAGES * stage_bytes;
+  uint64_t* b = reinterpret_cast<uint64_t*>(c.epi + 2 * A_STAGE_BYTES);
   c.full = b; c.empty = b + STAGES; c.tmem_full = b + 2 * STAGES; c.tmem_empty = b + 2 * STAGES + 2;
   c.tmem_ptr = reinterpret_cast<uint32_t*>(b + 2 * STAGES + 4);
   return c;
@@ -159,9 +129,10 @@ __device__ __forceinline__ SmemCtl carve(uint8_t* base, int stage_bytes) {
 // ===========================================================================
 // fprop / dgrad / dense:  out[M][n_out] = gather(src)[M][K] * Wk[n_out][K]^T
 // ===========================================================================
-template <typename T, typename To, int BN, bool A_TMA, bool SMALLC>
+template <typename T, typename To, int BN, bool A_TMA, bool SMALLC, bool TMA_EPI>
 __global__ void __launch_bounds__(A_TMA ? 192 : 320, 1)
-igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Geom g) {
+igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ CUtensorMap tmap_out, const Geom g) {
   using TL = Tile<BN>;
   constexpr int STAGES = TL::STAGES;
   constexpr bool TF32 = Elt<T>::TF32;
@@ -182,7 +153,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS); }
     fence_barrier_init();
   }
-  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmap_b); if (A_TMA) tma_prefetch_desc(&tmap_a); }
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tmap_b);
+    if (A_TMA) tma_prefetch_desc(&tmap_a);
+    if (TMA_EPI) tma_prefetch_desc(&tmap_out);
+  }
   if (warp == 4) tmem_alloc(ctl.tmem_ptr, TL::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -194,25 +169,91 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     // ------------------------------ epilogue ------------------------------
     int as = 0; uint32_t aphase = 0;
     To* out = reinterpret_cast<To*>(g.out);
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((g.ldc * (int)sizeof(To)) % 16 == 0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile / g.tiles_n, tn = tile - tm * g.tiles_n;
-      mbar_wait(&ctl.tmem_full[as], aphase, 10);
-      tc_fence_after();
-      const long long m = (long long)tm * 128 + warp * 32 + lane;
-      const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(warp * 32) << 16);
+    if (TMA_EPI) {
+      // TMEM -> registers -> 128B-swizzled smem tile [128 rows][128 B] -> TMA store (coalesced,
+      // rows >= M and columns >= n_out clipped by the tensor map).  Two staging tiles alternate.
+      constexpr int BOX_COLS = 128 / (int)sizeof(To);     // 64 (bf16) / 32 (fp32) output columns per store
+      constexpr int LDS_PER_BOX = BOX_COLS / 32;
+      constexpr int BOXES = BN / BOX_COLS;
+      uint32_t box_ctr = 0;
+      const int row = warp * 32 + lane;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / g.tiles_n, tn = tile - tm * g.tiles_n;
+        mbar_wait(&ctl.tmem_full[as], aphase, 10);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld32(tbase + c * 32, acc);
-        tmem_ld_wait();
-        const int n0 = tn * BN + c * 32;
-        const int valid = g.n_out - n0;
-        if (m < g.M && valid > 0) store_row32<To>(out + m * g.ldc + n0, acc, valid, vec_ok);
+        for (int b = 0; b < BOXES; ++b, ++box_ctr) {
+          uint8_t* stage = ctl.epi + (box_ctr & 1) * A_STAGE_BYTES;
+          const int n0 = tn * BN + b * BOX_COLS;
+          const bool live = n0 < g.n_out;                 // uniform across the CTA
+          if (live) {
+            if (threadIdx.x == 0) tma_store_wait_read<1>();   // the store issued two boxes ago has read its tile
+            named_barrier_sync(1, EPI_THREADS);
+          }
+          const uint32_t srow = smem_u32(stage);
+#pragma unroll
+          for (int h = 0; h < LDS_PER_BOX; ++h) {
+            uint32_t acc[32];
+            tmem_ld32(tbase + b * BOX_COLS + h * 32, acc);
+            tmem_ld_wait();
+            if (live) {
+              if (sizeof(To) == 2) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint32_t w[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(acc[8 * q + 2 * e]), __uint_as_float(acc[8 * q + 2 * e + 1]));
+                    w[e] = *reinterpret_cast<uint32_t*>(&hh);
+                  }
+                  sts16(srow + sw128_offset(row, h * 4 + q), make_uint4(w[0], w[1], w[2], w[3]));
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  sts16(srow + sw128_offset(row, q), make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+              }
+            }
+          }
+          if (b == BOXES - 1) { tc_fence_before(); mbar_arrive(&ctl.tmem_empty[as]); }   // accumulator drained
+          if (live) {
+            fence_proxy_async();
+            named_barrier_sync(1, EPI_THREADS);
+            if (threadIdx.x == 0) { tma_store_2d(&tmap_out, stage, n0, tm * 128); tma_store_commit(); }
+          }
+        }
+        as ^= 1; if (as == 0) aphase ^= 1;
       }
-      tc_fence_before();
-      mbar_arrive(&ctl.tmem_empty[as]);
-      as ^= 1; if (as == 0) aphase ^= 1;
+      if (threadIdx.x == 0) tma_store_wait_all<0>();
+    } else {
+      const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((g.ldc * (int)sizeof(To)) % 16 == 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / g.tiles_n, tn = tile - tm * g.tiles_n;
+        mbar_wait(&ctl.tmem_full[as], aphase, 10);
+        tc_fence_after();
+        const long long m = (long long)tm * 128 + warp * 32 + lane;
+        long long row_off = m * g.ldc;
+        if (g.os && m < g.M) {       // scattered rows (strided-dgrad parity class)
+          uint32_t n, rem, p, q;
+          g.dPQ.divmod((uint32_t)m, n, rem);
+          g.dQ.divmod(rem, p, q);
+          row_off = (((long long)n * g.OH + p * g.os + g.oh0) * g.OW + q * g.os + g.ow0) * g.ldc;
+        }
+        const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t acc[32];
+          tmem_ld32(tbase + c * 32, acc);
+          tmem_ld_wait();
+          const int n0 = tn * BN + c * 32;
+          const int valid = g.n_out - n0;
+          if (m < g.M && valid > 0) store_row32<To>(out + row_off + n0, acc, valid, vec_ok);
+        }
+        tc_fence_before();
+        mbar_arrive(&ctl.tmem_empty[as]);
+        as ^= 1; if (as == 0) aphase ^= 1;
+      }
     }
   } else if (warp == 4) {
     // ------------------------------ MMA issuer ----------------------------
@@ -253,7 +294,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           uint8_t* a_dst = smem + (size_t)pp.stage * TL::STAGE_BYTES;
           mbar_arrive_expect_tx(&ctl.full[pp.stage], TL::B_STAGE_BYTES + (A_TMA ? A_STAGE_BYTES : 0));
           if (A_TMA) tma_load_2d(a_dst, &tmap_a, &ctl.full[pp.stage], kb * KBE, tm * 128);
-          tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &ctl.full[pp.stage], kb * KBE, tn * BN);
+          int kcol = kb * KBE;
+          if (g.use_tab) { const int t = kb / g.cblocks; kcol = g.tab_kcol[t] + (kb - t * g.cblocks) * KBE; }
+          tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &ctl.full[pp.stage], kcol, tn * BN);
           advance<STAGES>(pp);
         }
       }
@@ -261,14 +304,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     __syncwarp();
   } else {
     // ------------------------------ gather producers ----------------------
+    // cp.async keeps GATHER_DEPTH K blocks of loads in flight per thread; a stage is handed to the
+    // MMA warp (fence.proxy.async + mbarrier arrive) once its group has landed.
     if (!A_TMA) {
+      constexpr int D = TL::GATHER_DEPTH;
       const int gt = threadIdx.x - 192;
       const int j = gt & 7;              // 16-byte chunk within the 128-byte K block
       const int row0 = gt >> 3;          // rows row0 + 16*i
-      Pipe pp{0, 0};
+      Pipe pi{0, 0}, pa{0, 0};
+      int inflight = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / g.tiles_n;
-        int rn[8], rbh[8], rbw[8];
+        int rpix[8], rbh[8], rbw[8];     // rpix: n*H*W of the gathered tensor (-1: row beyond M)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const long long m = (long long)tm * 128 + row0 + 16 * i;
@@ -276,25 +323,55 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             uint32_t n, rem, p, q;
             g.dPQ.divmod((uint32_t)m, n, rem);
             g.dQ.divmod(rem, p, q);
-            rn[i] = (int)n;
+            rpix[i] = (int)n * g.H * g.W;
             rbh[i] = g.mode == 0 ? (int)p * g.stride - g.pad_h : (int)p + g.pad_h;
             rbw[i] = g.mode == 0 ? (int)q * g.stride - g.pad_w : (int)q + g.pad_w;
-          } else { rn[i] = -1; rbh[i] = 0; rbw[i] = 0; }
+          } else { rpix[i] = -1; rbh[i] = 0; rbw[i] = 0; }
         }
+        const T* src = reinterpret_cast<const T*>(g.src);
         for (int kb = 0; kb < g.num_kb; ++kb) {
           const uint32_t k0 = (uint32_t)(kb * KBE + j * CH);
-          uint4 v[8];
+          mbar_wait(&ctl.empty[pi.stage], pi.phase ^ 1, 40);
+          const uint32_t a_addr = smem_u32(smem + (size_t)pi.stage * TL::STAGE_BYTES);
+          if (!SMALLC) {
+            uint32_t tap, c; g.dC.divmod(k0, tap, c);
+            const TapRef t = decode_tap(g, tap);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = gather_chunk<T, SMALLC>(g, rn[i], rbh[i], rbw[i], k0);
-          mbar_wait(&ctl.empty[pp.stage], pp.phase ^ 1, 40);
-          const uint32_t a_addr = smem_u32(smem + (size_t)pp.stage * TL::STAGE_BYTES);
+            for (int i = 0; i < 8; ++i) {
+              const int h = rbh[i] + t.dr, w = rbw[i] + t.ds;
+              const bool ok = t.ok && rpix[i] >= 0 && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W;
+              const T* p = src + (long long)(rpix[i] + h * g.W + w) * g.C + c;
+              cp_async16(a_addr + sw128_offset(row0 + 16 * i, j), ok ? (const void*)p : (const void*)src, ok ? 16u : 0u);
+            }
+          } else {
+            // stem: 4 stored channels, so a 16-byte chunk covers two taps (8 bytes each)
+            const TapRef t0 = decode_tap(g, k0 >> 2), t1 = decode_tap(g, (k0 >> 2) + 1);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sts16(a_addr + sw128_offset(row0 + 16 * i, j), v[i]);
-          fence_proxy_async();
-          mbar_arrive(&ctl.full[pp.stage]);
-          advance<STAGES>(pp);
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t dst = a_addr + sw128_offset(row0 + 16 * i, j);
+              const int h0 = rbh[i] + t0.dr, w0 = rbw[i] + t0.ds, h1 = rbh[i] + t1.dr, w1 = rbw[i] + t1.ds;
+              const bool ok0 = t0.ok && rpix[i] >= 0 && (unsigned)h0 < (unsigned)g.H && (unsigned)w0 < (unsigned)g.W;
+              const bool ok1 = t1.ok && rpix[i] >= 0 && (unsigned)h1 < (unsigned)g.H && (unsigned)w1 < (unsigned)g.W;
+              const T* p0 = src + (long long)(rpix[i] + h0 * g.W + w0) * 4;
+              const T* p1 = src + (long long)(rpix[i] + h1 * g.W + w1) * 4;
+              cp_async8(dst, ok0 ? (const void*)p0 : (const void*)src, ok0 ? 8u : 0u);
+              cp_async8(dst + 8, ok1 ? (const void*)p1 : (const void*)src, ok1 ? 8u : 0u);
+            }
+          }
+          cp_async_commit();
+          advance<STAGES>(pi);
+          if (++inflight == D) {
+            cp_async_wait<D - 1>();
+            fence_proxy_async();
+            mbar_arrive(&ctl.full[pa.stage]);
+            advance<STAGES>(pa);
+            --inflight;
+          }
         }
       }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      for (; inflight > 0; --inflight) { mbar_arrive(&ctl.full[pa.stage]); advance<STAGES>(pa); }
     }
   }
 
@@ -308,9 +385,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 // A^T (activations) and B (dY) are both MN-major: the reduction runs over pixels.
 // Work item = (128 k-rows) x (BN couts) x (pixel split); fp32 atomics combine splits.
 // ===========================================================================
-template <typename T, int BN, bool SMALLC>
-__global__ void __launch_bounds__(320, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const Geom g, float* __restrict__ dw) {
+template <typename T, int BN, bool SMALLC, bool A_TMA>
+__global__ void __launch_bounds__(A_TMA ? 192 : 320, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const Geom g,
+             float* __restrict__ dw) {
   using TL = Tile<BN>;
   constexpr int STAGES = TL::STAGES;
   constexpr bool TF32 = Elt<T>::TF32;
@@ -330,11 +408,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const Geom g, float* _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl.full[s], 1 + GATHER_THREADS); mbar_init(&ctl.empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl.full[s], A_TMA ? 1 : 1 + GATHER_THREADS); mbar_init(&ctl.empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS); }
     fence_barrier_init();
   }
-  if (warp == 5 && lane == 0) tma_prefetch_desc(&tmap_dy);
+  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmap_dy); if (A_TMA) tma_prefetch_desc(&tmap_x); }
   if (warp == 4) tmem_alloc(ctl.tmem_ptr, TL::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -416,8 +494,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const Geom g, float* _
         int tk, tn, kb0, kb1; decode(item, tk, tn, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&ctl.empty[pp.stage], pp.phase ^ 1, 70);
-          uint8_t* b_dst = smem + (size_t)pp.stage * TL::STAGE_BYTES + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&ctl.full[pp.stage], TL::B_STAGE_BYTES);
+          uint8_t* a_dst = smem + (size_t)pp.stage * TL::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&ctl.full[pp.stage], TL::B_STAGE_BYTES + (A_TMA ? A_STAGE_BYTES : 0));
+          if (A_TMA) {     // 1x1 stride-1: the activation tile is a plain [pixels][channels] box
+#pragma unroll
+            for (int a = 0; a < A_ATOMS; ++a)
+              tma_load_2d(a_dst + a * ATOM_BYTES, &tmap_x, &ctl.full[pp.stage], tk * 128 + a * ATOM_E, kb * PXS);
+          }
 #pragma unroll
           for (int a = 0; a < B_ATOMS; ++a)
             tma_load_2d(b_dst + a * ATOM_BYTES, &tmap_dy, &ctl.full[pp.stage], tn * BN + a * ATOM_E, kb * PXS);
@@ -426,68 +510,79 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const Geom g, float* _
       }
     }
     __syncwarp();
-  } else {
+  } else if (!A_TMA) {
+    constexpr int D = TL::GATHER_DEPTH;
     const int gt = threadIdx.x - 192;
     const int j = gt & 7;
-    Pipe pp{0, 0};
+    Pipe pi{0, 0}, pa{0, 0};
+    int inflight = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int tk, tn, kb0, kb1; decode(item, tk, tn, kb0, kb1);
       // piece i of this thread: q = gt/8 + 16*i -> atom q / PXS, pixel q % PXS; its (tap, c) is fixed per item
-      int pr[8], ps[8], pc[8]; bool pk[8];
-      int pr2[8], ps2[8]; bool pk2[8];
+      int pdr[8], pds[8], pc[8]; bool pk[8];
+      int pdr2[8], pds2[8]; bool pk2[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int q = (gt >> 3) + 16 * i;
         const int atom = q / PXS;
         const uint32_t k = (uint32_t)(tk * 128 + atom * ATOM_E + j * CH);
         if (!SMALLC) {
-          uint32_t tap, c, r, s; g.dC.divmod(k, tap, c); g.dS.divmod(tap, r, s);
-          pk[i] = (int)tap < g.RS; pr[i] = (int)r; ps[i] = (int)s; pc[i] = (int)c;
-          pk2[i] = false; pr2[i] = ps2[i] = 0;
+          uint32_t tap, c; g.dC.divmod(k, tap, c);
+          const TapRef t = decode_tap(g, tap);
+          pk[i] = t.ok; pdr[i] = t.dr; pds[i] = t.ds; pc[i] = (int)c;
+          pk2[i] = false; pdr2[i] = pds2[i] = 0;
         } else {
-          const uint32_t tap0 = k >> 2;
-          uint32_t r, s; g.dS.divmod(tap0, r, s);
-          pk[i] = (int)tap0 < g.RS; pr[i] = (int)r; ps[i] = (int)s; pc[i] = 0;
-          g.dS.divmod(tap0 + 1, r, s);
-          pk2[i] = (int)(tap0 + 1) < g.RS; pr2[i] = (int)r; ps2[i] = (int)s;
+          const TapRef t0 = decode_tap(g, k >> 2), t1 = decode_tap(g, (k >> 2) + 1);
+          pk[i] = t0.ok; pdr[i] = t0.dr; pds[i] = t0.ds; pc[i] = 0;
+          pk2[i] = t1.ok; pdr2[i] = t1.dr; pds2[i] = t1.ds;
         }
       }
+      const T* src = reinterpret_cast<const T*>(g.src);
       for (int kb = kb0; kb < kb1; ++kb) {
-        uint4 v[8];
+        mbar_wait(&ctl.empty[pi.stage], pi.phase ^ 1, 80);
+        const uint32_t a_addr = smem_u32(smem + (size_t)pi.stage * TL::STAGE_BYTES);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int q = (gt >> 3) + 16 * i;
           const int px = q % PXS;
+          const uint32_t dst = a_addr + (q / PXS) * ATOM_BYTES + sw128_offset(px, j);
           const long long m = (long long)kb * PXS + px;
-          v[i] = make_uint4(0, 0, 0, 0);
+          int pix = -1, bh = 0, bw = 0;
           if (m < g.M) {
-            uint32_t n, rem, p, qq;
-            g.dPQ.divmod((uint32_t)m, n, rem);
+            uint32_t nn, rem, p, qq;
+            g.dPQ.divmod((uint32_t)m, nn, rem);
             g.dQ.divmod(rem, p, qq);
-            const int bh = (int)p * g.stride - g.pad_h, bw = (int)qq * g.stride - g.pad_w;
-            if (!SMALLC) {
-              if (pk[i]) {
-                const T* src = src_pixel<T>(g, (int)n, bh, bw, pr[i], ps[i]);
-                if (src) v[i] = ldg16(src + pc[i]);
-              }
-            } else {
-              if (pk[i]) { const T* src = src_pixel<T>(g, (int)n, bh, bw, pr[i], ps[i]); if (src) { const uint2 u = ldg8(src); v[i].x = u.x; v[i].y = u.y; } }
-              if (pk2[i]) { const T* src = src_pixel<T>(g, (int)n, bh, bw, pr2[i], ps2[i]); if (src) { const uint2 u = ldg8(src); v[i].z = u.x; v[i].w = u.y; } }
-            }
+            pix = (int)nn * g.H * g.W; bh = (int)p * g.stride - g.pad_h; bw = (int)qq * g.stride - g.pad_w;
+          }
+          if (!SMALLC) {
+            const int h = bh + pdr[i], w = bw + pds[i];
+            const bool ok = pk[i] && pix >= 0 && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W;
+            const T* p = src + (long long)(pix + h * g.W + w) * g.C + pc[i];
+            cp_async16(dst, ok ? (const void*)p : (const void*)src, ok ? 16u : 0u);
+          } else {
+            const int h0 = bh + pdr[i], w0 = bw + pds[i], h1 = bh + pdr2[i], w1 = bw + pds2[i];
+            const bool ok0 = pk[i] && pix >= 0 && (unsigned)h0 < (unsigned)g.H && (unsigned)w0 < (unsigned)g.W;
+            const bool ok1 = pk2[i] && pix >= 0 && (unsigned)h1 < (unsigned)g.H && (unsigned)w1 < (unsigned)g.W;
+            const T* p0 = src + (long long)(pix + h0 * g.W + w0) * 4;
+            const T* p1 = src + (long long)(pix + h1 * g.W + w1) * 4;
+            cp_async8(dst, ok0 ? (const void*)p0 : (const void*)src, ok0 ? 8u : 0u);
+            cp_async8(dst + 8, ok1 ? (const void*)p1 : (const void*)src, ok1 ? 8u : 0u);
           }
         }
-        mbar_wait(&ctl.empty[pp.stage], pp.phase ^ 1, 80);
-        const uint32_t a_addr = smem_u32(smem + (size_t)pp.stage * TL::STAGE_BYTES);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int q = (gt >> 3) + 16 * i;
-          sts16(a_addr + (q / PXS) * ATOM_BYTES + sw128_offset(q % PXS, j), v[i]);
+        cp_async_commit();
+        advance<STAGES>(pi);
+        if (++inflight == D) {
+          cp_async_wait<D - 1>();
+          fence_proxy_async();
+          mbar_arrive(&ctl.full[pa.stage]);
+          advance<STAGES>(pa);
+          --inflight;
         }
-        fence_proxy_async();
-        mbar_arrive(&ctl.full[pp.stage]);
-        advance<STAGES>(pp);
       }
     }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (; inflight > 0; --inflight) { mbar_arrive(&ctl.full[pa.stage]); advance<STAGES>(pa); }
   }
 
   tc_fence_before();
@@ -506,28 +601,35 @@ template <typename K> int set_smem_attr(K kernel, size_t bytes) {
   return SIMCLR_OK;
 }
 
-template <typename T, typename To, int BN, bool A_TMA, bool SMALLC>
-int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, cudaStream_t st) {
-  auto kern = igemm_kernel<T, To, BN, A_TMA, SMALLC>;
+template <typename T, typename To, int BN, bool A_TMA, bool SMALLC, bool TMA_EPI>
+int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const Geom& g, cudaStream_t st) {
+  auto kern = igemm_kernel<T, To, BN, A_TMA, SMALLC, TMA_EPI>;
   static bool attr = false;
   if (!attr) { int rc = set_smem_attr(kern, Tile<BN>::SMEM_BYTES); if (rc) return rc; attr = true; }
   int grid = g.tiles_m * g.tiles_n; if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, A_TMA ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(ta, tb, g);
+  kern<<<grid, A_TMA ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(ta, tb, tout, g);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
 
-template <typename T, typename To, int BN>
-int dispatch_igemm2(bool a_tma, bool smallc, const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, cudaStream_t st) {
-  if (a_tma) return launch_igemm<T, To, BN, true, false>(ta, tb, g, st);
-  if (smallc) return launch_igemm<T, To, BN, false, true>(ta, tb, g, st);
-  return launch_igemm<T, To, BN, false, false>(ta, tb, g, st);
+template <typename T, typename To, int BN, bool TMA_EPI>
+int dispatch_igemm2(bool a_tma, bool smallc, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                    const Geom& g, cudaStream_t st) {
+  if (a_tma) return launch_igemm<T, To, BN, true, false, TMA_EPI>(ta, tb, tout, g, st);
+  if (smallc) return launch_igemm<T, To, BN, false, true, TMA_EPI>(ta, tb, tout, g, st);
+  return launch_igemm<T, To, BN, false, false, TMA_EPI>(ta, tb, tout, g, st);
 }
 template <typename T, typename To>
-int dispatch_igemm(int bn, bool a_tma, bool smallc, const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, cudaStream_t st) {
-  if (bn == 256) return dispatch_igemm2<T, To, 256>(a_tma, smallc, ta, tb, g, st);
-  if (bn == 128) return dispatch_igemm2<T, To, 128>(a_tma, smallc, ta, tb, g, st);
-  return dispatch_igemm2<T, To, 64>(a_tma, smallc, ta, tb, g, st);
+int dispatch_igemm(int bn, bool a_tma, bool smallc, bool tma_epi, const CUtensorMap& ta, const CUtensorMap& tb,
+                   const CUtensorMap& tout, const Geom& g, cudaStream_t st) {
+  if (tma_epi) {
+    if (bn == 256) return dispatch_igemm2<T, To, 256, true>(a_tma, smallc, ta, tb, tout, g, st);
+    if (bn == 128) return dispatch_igemm2<T, To, 128, true>(a_tma, smallc, ta, tb, tout, g, st);
+    return dispatch_igemm2<T, To, 64, true>(a_tma, smallc, ta, tb, tout, g, st);
+  }
+  if (bn == 256) return dispatch_igemm2<T, To, 256, false>(a_tma, smallc, ta, tb, tout, g, st);
+  if (bn == 128) return dispatch_igemm2<T, To, 128, false>(a_tma, smallc, ta, tb, tout, g, st);
+  return dispatch_igemm2<T, To, 64, false>(a_tma, smallc, ta, tb, tout, g, st);
 }
 
 // Shared driver for fprop (mode 0) and dgrad (mode 1).
@@ -553,40 +655,119 @@ int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, i
   g.M = M; g.n_out = (int)n_out; g.ldc = (int)n_out; g.num_kb = (int)(Kp / KBE);
   g.tiles_m = (int)((M + 127) / 128); g.tiles_n = (int)((n_out + bn - 1) / bn);
   g.Cin = g.Cout = 0; g.splits = 1; g.kb_per_split = g.num_kb;
+  g.use_tab = 0; g.cblocks = 1; g.os = 0; g.oh0 = g.ow0 = 0; g.OH = g.OW = 0;
+  g.tap_sign = mode == 0 ? 1 : -1;
   // plain GEMM (1x1, stride 1, no padding): activations go through TMA as well
   const bool a_tma = (R == 1 && S == 1 && stride == 1 && !smallc && (Cs * es) % 16 == 0);
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tout;
   int rc = make_tmap_2d(&tb, wk, es, (uint64_t)n_out, (uint64_t)Kp, (uint64_t)Kp * es, (uint32_t)bn, (uint32_t)KBE);
   if (rc) return rc;
   if (a_tma) { rc = make_tmap_2d(&ta, src, es, (uint64_t)M, (uint64_t)Cs, (uint64_t)Cs * es, 128, (uint32_t)KBE); if (rc) return rc; }
   else ta = tb;
-  if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_BF16) return dispatch_igemm<__nv_bfloat16, __nv_bfloat16>(bn, a_tma, smallc, ta, tb, g, st);
-  if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_F32) return dispatch_igemm<__nv_bfloat16, float>(bn, a_tma, smallc, ta, tb, g, st);
-  if (dtype == SIMCLR_F32 && out_dtype == SIMCLR_F32) return dispatch_igemm<float, float>(bn, a_tma, smallc, ta, tb, g, st);
+  // coalesced TMA-store epilogue whenever the output rows are 16-byte aligned
+  const int eo = out_dtype == SIMCLR_BF16 ? 2 : 4;
+  const bool tma_epi = aligned16(out) && ((n_out * eo) % 16 == 0);
+  if (tma_epi) { rc = make_tmap_2d(&tout, out, eo, (uint64_t)M, (uint64_t)n_out, (uint64_t)n_out * eo, 128, (uint32_t)(128 / eo)); if (rc) return rc; }
+  else tout = tb;
+  if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_BF16) return dispatch_igemm<__nv_bfloat16, __nv_bfloat16>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st);
+  if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_F32) return dispatch_igemm<__nv_bfloat16, float>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st);
+  if (dtype == SIMCLR_F32 && out_dtype == SIMCLR_F32) return dispatch_igemm<float, float>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st);
   set_error("%s: unsupported dtype combination %d -> %d", what, dtype, out_dtype);
   return SIMCLR_ERR_UNSUPPORTED;
 }
 
-template <typename T, int BN, bool SMALLC>
-int launch_wgrad(const CUtensorMap& tdy, const Geom& g, float* dw, cudaStream_t st) {
-  auto kern = wgrad_kernel<T, BN, SMALLC>;
+// dgrad of a strided conv, decomposed by output-pixel parity: the pixels of dX with
+// (h mod s, w mod s) == (ph, pw) only receive the taps with (ph + pad - r) % s == 0, reading
+// dY at h/s + (ph + pad - r)/s.  Each class is a dense stride-1 gather over the dY grid with its
+// own tap list -- no multiplications by structural zeros (a stride-2 3x3 does 9/4 of the dense
+// work instead of 9x).  Classes without taps (1x1 kernels) stay zero from the memset.
+int run_dgrad_strided(const void* dy, const void* wd, void* dx, int dtype, int out_dtype, int64_t N, int64_t H,
+                      int64_t W, int64_t Cin, int64_t Cout, int64_t R, int64_t S, int64_t stride, cudaStream_t st) {
+  const int es = dtype == SIMCLR_BF16 ? 2 : 4;
+  const int eo = out_dtype == SIMCLR_BF16 ? 2 : 4;
+  const int KBE = 128 / es;
+  const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int pad_h = (int)((R - 1) / 2), pad_w = (int)((S - 1) / 2);
+  const int64_t Kdp = (R * S * Cout + KBE - 1) / KBE * KBE;
+  const int bn = pick_bn(Cin);
+  CUtensorMap tb;
+  int rc = make_tmap_2d(&tb, wd, es, (uint64_t)Cin, (uint64_t)Kdp, (uint64_t)Kdp * es, (uint32_t)bn, (uint32_t)KBE);
+  if (rc) return rc;
+  bool need_zero = false;
+  for (int ph = 0; ph < stride; ++ph) {
+    int cnt = 0;
+    for (int r = 0; r < R; ++r) if ((ph + pad_h - r) % (int)stride == 0) ++cnt;
+    if (cnt == 0) need_zero = true;
+  }
+  for (int pw = 0; pw < stride; ++pw) {
+    int cnt = 0;
+    for (int s2 = 0; s2 < S; ++s2) if ((pw + pad_w - s2) % (int)stride == 0) ++cnt;
+    if (cnt == 0) need_zero = true;
+  }
+  if (need_zero) SIMCLR_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)(N * H * W * Cin) * eo, st));
+  for (int ph = 0; ph < stride; ++ph) {
+    for (int pw = 0; pw < stride; ++pw) {
+      Geom g;
+      int nt = 0;
+      for (int r = 0; r < R; ++r) {
+        if ((ph + pad_h - r) % (int)stride != 0) continue;
+        for (int s2 = 0; s2 < S; ++s2) {
+          if ((pw + pad_w - s2) % (int)stride != 0) continue;
+          if (nt >= 9) { set_error("conv2d_dgrad_tc: too many taps per parity class"); return SIMCLR_ERR_UNSUPPORTED; }
+          // C division truncates toward zero; the numerator is an exact multiple of the stride
+          g.tab_r[nt] = (ph + pad_h - r) / (int)stride;
+          g.tab_s[nt] = (pw + pad_w - s2) / (int)stride;
+          g.tab_kcol[nt] = (int)((r * S + s2) * Cout);
+          ++nt;
+        }
+      }
+      const int64_t P2 = (H - ph + stride - 1) / stride, Q2 = (W - pw + stride - 1) / stride;
+      if (nt == 0 || P2 <= 0 || Q2 <= 0) continue;
+      for (int t = nt; t < 9; ++t) { g.tab_r[t] = g.tab_s[t] = 0; g.tab_kcol[t] = 0; }
+      const int64_t M = N * P2 * Q2;
+      g.src = dy; g.out = dx; g.mode = 0;
+      g.H = (int)Ho; g.W = (int)Wo; g.C = (int)Cout; g.R = 1; g.S = 1; g.RS = nt;
+      g.stride = 1; g.pad_h = 0; g.pad_w = 0;
+      g.dPQ = FastDiv((uint32_t)(P2 * Q2)); g.dQ = FastDiv((uint32_t)Q2); g.dC = FastDiv((uint32_t)Cout); g.dS = FastDiv(1);
+      g.M = M; g.n_out = (int)Cin; g.ldc = (int)Cin;
+      g.cblocks = (int)(Cout / KBE); g.num_kb = nt * g.cblocks;
+      g.tiles_m = (int)((M + 127) / 128); g.tiles_n = (int)((Cin + bn - 1) / bn);
+      g.Cin = g.Cout = 0; g.splits = 1; g.kb_per_split = g.num_kb;
+      g.tap_sign = 1;
+      g.use_tab = 1; g.os = (int)stride; g.oh0 = ph; g.ow0 = pw; g.OH = (int)H; g.OW = (int)W;
+      if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_BF16) rc = dispatch_igemm<__nv_bfloat16, __nv_bfloat16>(bn, false, false, false, tb, tb, tb, g, st);
+      else if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_F32) rc = dispatch_igemm<__nv_bfloat16, float>(bn, false, false, false, tb, tb, tb, g, st);
+      else if (dtype == SIMCLR_F32 && out_dtype == SIMCLR_F32) rc = dispatch_igemm<float, float>(bn, false, false, false, tb, tb, tb, g, st);
+      else { set_error("conv2d_dgrad_tc: unsupported dtype combination"); return SIMCLR_ERR_UNSUPPORTED; }
+      if (rc) return rc;
+    }
+  }
+  return SIMCLR_OK;
+}
+
+template <typename T, int BN, bool SMALLC, bool A_TMA>
+int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, const Geom& g, float* dw, cudaStream_t st) {
+  auto kern = wgrad_kernel<T, BN, SMALLC, A_TMA>;
   static bool attr = false;
   if (!attr) { int rc = set_smem_attr(kern, Tile<BN>::SMEM_BYTES); if (rc) return rc; attr = true; }
   int grid = g.tiles_m * g.tiles_n * g.splits; if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, 320, Tile<BN>::SMEM_BYTES, st>>>(tdy, g, dw);
+  kern<<<grid, A_TMA ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(tx, tdy, g, dw);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
+template <typename T, int BN>
+int dispatch_wgrad2(bool smallc, bool a_tma, const CUtensorMap& tx, const CUtensorMap& tdy, const Geom& g, float* dw,
+                    cudaStream_t st) {
+  if (a_tma) return launch_wgrad<T, BN, false, true>(tx, tdy, g, dw, st);
+  if (smallc) return launch_wgrad<T, BN, true, false>(tx, tdy, g, dw, st);
+  return launch_wgrad<T, BN, false, false>(tx, tdy, g, dw, st);
+}
 template <typename T>
-int dispatch_wgrad(int bn, bool smallc, const CUtensorMap& tdy, const Geom& g, float* dw, cudaStream_t st) {
-  if (smallc) {
-    if (bn == 256) return launch_wgrad<T, 256, true>(tdy, g, dw, st);
-    if (bn == 128) return launch_wgrad<T, 128, true>(tdy, g, dw, st);
-    return launch_wgrad<T, 64, true>(tdy, g, dw, st);
-  }
-  if (bn == 256) return launch_wgrad<T, 256, false>(tdy, g, dw, st);
-  if (bn == 128) return launch_wgrad<T, 128, false>(tdy, g, dw, st);
-  return launch_wgrad<T, 64, false>(tdy, g, dw, st);
+int dispatch_wgrad(int bn, bool smallc, bool a_tma, const CUtensorMap& tx, const CUtensorMap& tdy, const Geom& g,
+                   float* dw, cudaStream_t st) {
+  if (bn == 256) return dispatch_wgrad2<T, 256>(smallc, a_tma, tx, tdy, g, dw, st);
+  if (bn == 128) return dispatch_wgrad2<T, 128>(smallc, a_tma, tx, tdy, g, dw, st);
+  return dispatch_wgrad2<T, 64>(smallc, a_tma, tx, tdy, g, dw, st);
 }
 
 }  // namespace
@@ -613,6 +794,16 @@ int simclr_conv2d_dgrad_tc(const void* dy, const void* wd, void* dx, int dtype, 
   SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
                    "conv2d_dgrad_tc: bad geometry");
   const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  {
+    const int es = dtype == SIMCLR_BF16 ? 2 : 4;
+    if (stride > 1 && stride <= 3 && Cout % (128 / es) == 0 && simclr::aligned16(dy) && simclr::aligned16(wd) && simclr::aligned16(dx))
+      return tc::run_dgrad_strided(dy, wd, dx, dtype, dx_dtype, N, H, W, Cin, Cout, R, S, stride, (cudaStream_t)stream);
+    if (stride > 1) {
+      simclr::set_error("conv2d_dgrad_tc: stride %lld needs Cout %% %d == 0, stride <= 3 and 16-byte aligned operands",
+                        (long long)stride, 128 / es);
+      return SIMCLR_ERR_UNSUPPORTED;
+    }
+  }
   // gathered tensor is dY [N][Ho][Wo][Cout]; GEMM rows are the pixels of dX
   return tc::run_igemm(1, dy, wd, dx, dtype, dx_dtype, N, Ho, Wo, Cout, H, W, Cin, R, S, stride, (cudaStream_t)stream,
                        "conv2d_dgrad_tc");
@@ -651,6 +842,7 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   g.num_kb = (int)((M + pxs - 1) / pxs);
   g.tiles_m = (int)((R * S * Cs + 127) / 128); g.tiles_n = (int)((Cout + bn - 1) / bn);
   g.Cin = (int)Cin; g.Cout = (int)Cout;
+  g.use_tab = 0; g.cblocks = 1; g.os = 0; g.oh0 = g.ow0 = 0; g.OH = g.OW = 0; g.tap_sign = 1;
   const int tiles = g.tiles_m * g.tiles_n;
   int splits = (2 * num_sms() + tiles - 1) / tiles;
   const int max_splits = g.num_kb / 8 > 0 ? g.num_kb / 8 : 1;
@@ -658,11 +850,14 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   if (splits < 1) splits = 1;
   g.kb_per_split = (g.num_kb + splits - 1) / splits;
   g.splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;
-  CUtensorMap tdy;
+  CUtensorMap tdy, tx;
   int rc = make_tmap_2d(&tdy, dy, es, (uint64_t)M, (uint64_t)Cout, (uint64_t)Cout * es, (uint32_t)pxs, (uint32_t)ATOM_E);
   if (rc) return rc;
+  const bool a_tma = (R == 1 && S == 1 && stride == 1 && !smallc && (Cs * es) % 16 == 0);
+  if (a_tma) { rc = make_tmap_2d(&tx, x, es, (uint64_t)M, (uint64_t)Cs, (uint64_t)Cs * es, (uint32_t)pxs, (uint32_t)ATOM_E); if (rc) return rc; }
+  else tx = tdy;
   SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(R * S * Cin * Cout) * sizeof(float), st));
-  if (dtype == SIMCLR_BF16) return dispatch_wgrad<__nv_bfloat16>(bn, smallc, tdy, g, dw, st);
+  if (dtype == SIMCLR_BF16) return dispatch_wgrad<__nv_bfloat16>(bn, smallc, a_tma, tx, tdy, g, dw, st);
   set_error("conv2d_wgrad_tc: unknown dtype %d", dtype);
   return SIMCLR_ERR_INVALID_ARG;
 }
