@@ -221,6 +221,26 @@ SIMCLR_API int simclr_input_prep(const float* features, void* out, int dtype, in
                                  int64_t W, int64_t T, int use_blur, int64_t blur_kernel_size,
                                  const float* sigma, const uint8_t* selector, float* tmp, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Train-time augmentation on device (tf2/data_util.py:443-475 preprocess_for_train):
+ * crop (box from sample_distorted_bounding_box, supplied by the caller) + bicubic
+ * resize (tf.image.resize BICUBIC semantics), random_flip_left_right, random_color_jitter
+ * (brightness / contrast / saturation / hue in a drawn order, clip after each),
+ * grayscale, final clip.  Every tf.random draw is an input.
+ *   src        uint8 images [Hs,Ws,3] packed back to back; image i starts at src + src_offset[i]
+ *   src_hw     [n][2] int32 {Hs, Ws};  box [n][4] int32 {y, x, h, w};  flip [n] bytes
+ *   colour     [n][8] floats {apply_jitter, perm code (op_t = (code >> 2t) & 3; 0 brightness,
+ *              1 contrast, 2 saturation, 3 hue), brightness factor, contrast factor,
+ *              saturation factor, hue delta, apply_gray, unused}
+ *   out        fp32; pixel (i, y, x) channel c at out[((i*height + y)*width + x)*out_pixel_stride
+ *              + out_channel_offset + c]  (stride 6 / offsets 0 and 3 write the two views of
+ *              tf2/data.py:55-58 straight into the [B,H,W,6] feature tensor)
+ * ------------------------------------------------------------------------- */
+SIMCLR_API int simclr_augment(const uint8_t* src, const int64_t* src_offset, const int32_t* src_hw,
+                              const int32_t* box, const uint8_t* flip, const float* colour, float* out,
+                              int64_t n, int64_t height, int64_t width, int64_t out_pixel_stride,
+                              int64_t out_channel_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

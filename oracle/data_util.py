@@ -178,7 +178,7 @@ def _bicubic_axis_weights(in_size, out_size, dtype):
             if 0 <= idx < in_size:
                 W[o, idx] += w[t]
                 tot += float(w[t])
-        if abs(tot) > 1000.0 * 1.1920929e-07:
+        if abs(tot) >= 1000.0 * 1.17549435e-38:      # std::numeric_limits<float>::min(), as in TF's kernel
             W[o] /= tot
     return W.to(dtype)
 

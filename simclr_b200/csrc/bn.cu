@@ -217,7 +217,8 @@ int launch_reduce(void* a, const void* a2, const void* zmask, const void* y, int
                   const float* mean, const float* rstd, double* sums, cudaStream_t st) {
   const RedLayout l = red_layout(C);
   int64_t nblocks = (rows + l.row_lanes * 8 - 1) / (l.row_lanes * 8);
-  const int64_t cap = (int64_t)num_sms() * 8;
+  // 3 CTAs of 256 threads are resident per SM (64-74 registers): a multiple of 3*SMs avoids a ragged last wave
+  const int64_t cap = (int64_t)num_sms() * 12;
   if (nblocks > cap) nblocks = cap;
   if (nblocks < 1) nblocks = 1;
   const int rows_per_block = (int)((rows + nblocks - 1) / nblocks);

@@ -45,6 +45,8 @@ struct Geom {
   int Cin, Cout, splits, kb_per_split;
   // strided-dgrad parity classes: taps from a table, output rows scattered with stride `os`
   int use_tab, cblocks;
+  int P, Q;            // GEMM-row pixel grid (wgrad: incremental pixel walk)
+  int adv_p, adv_q;    // pixels-per-stage / Q and % Q
   int tap_sign;        // +1: source = base + (r, s) (fprop / wgrad / tables); -1: base - (r, s) (stride-1 dgrad)
   int tab_r[9], tab_s[9], tab_kcol[9];
   int os, oh0, ow0, OH, OW;
@@ -385,10 +387,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 // A^T (activations) and B (dY) are both MN-major: the reduction runs over pixels.
 // Work item = (128 k-rows) x (BN couts) x (pixel split); fp32 atomics combine splits.
 // ===========================================================================
-template <typename T, int BN, bool SMALLC, bool A_TMA>
+template <typename T, int BN, bool SMALLC, bool A_TMA, bool TMA_RED>
 __global__ void __launch_bounds__(A_TMA ? 192 : 320, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const Geom g,
-             float* __restrict__ dw) {
+wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+             const __grid_constant__ CUtensorMap tmap_dw, const Geom g, float* __restrict__ dw) {
   using TL = Tile<BN>;
   constexpr int STAGES = TL::STAGES;
   constexpr bool TF32 = Elt<T>::TF32;
@@ -412,7 +414,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS); }
     fence_barrier_init();
   }
-  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmap_dy); if (A_TMA) tma_prefetch_desc(&tmap_x); }
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tmap_dy);
+    if (A_TMA) tma_prefetch_desc(&tmap_x);
+    if (TMA_RED) tma_prefetch_desc(&tmap_dw);
+  }
   if (warp == 4) tmem_alloc(ctl.tmem_ptr, TL::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -431,32 +437,62 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
 
   if (warp < 4) {
     int as = 0; uint32_t aphase = 0;
+    uint32_t box_ctr = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int tk, tn, kb0, kb1; decode(item, tk, tn, kb0, kb1);
       if (kb0 >= kb1) continue;
       mbar_wait(&ctl.tmem_full[as], aphase, 50);
       tc_fence_after();
-      const int k = tk * 128 + warp * 32 + lane;           // row of the [R*S*Cs][Cout] matrix
-      uint32_t tap, c; g.dC.divmod((uint32_t)k, tap, c);
-      const bool row_ok = (int)tap < g.RS && (int)c < g.Cin;
-      float* drow = dw + ((long long)tap * g.Cin + c) * g.Cout;
       const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(warp * 32) << 16);
+      if (TMA_RED) {
+        // partial tile -> swizzled smem [128 k-rows][32 fp32] -> TMA reduce-add into dW (splits combine at L2)
+        const int row = warp * 32 + lane;
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        uint32_t acc[32];
-        tmem_ld32(tbase + cc * 32, acc);
-        tmem_ld_wait();
-        const int n0 = tn * BN + cc * 32;
-        if (row_ok) {
+        for (int cc = 0; cc < BN / 32; ++cc, ++box_ctr) {
+          uint8_t* stage = ctl.epi + (box_ctr & 1) * A_STAGE_BYTES;
+          const int n0 = tn * BN + cc * 32;
+          const bool live = n0 < g.Cout;
+          if (live) {
+            if (threadIdx.x == 0) tma_store_wait_read<1>();
+            named_barrier_sync(1, EPI_THREADS);
+          }
+          uint32_t acc[32];
+          tmem_ld32(tbase + cc * 32, acc);
+          tmem_ld_wait();
+          if (cc == BN / 32 - 1) { tc_fence_before(); mbar_arrive(&ctl.tmem_empty[as]); }
+          if (live) {
+            const uint32_t srow = smem_u32(stage);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n0 + i < g.Cout) atomicAdd(drow + n0 + i, __uint_as_float(acc[i]));
+            for (int q = 0; q < 8; ++q)
+              sts16(srow + sw128_offset(row, q), make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+            fence_proxy_async();
+            named_barrier_sync(1, EPI_THREADS);
+            if (threadIdx.x == 0) { tma_reduce_add_2d(&tmap_dw, stage, n0, tk * 128); tma_store_commit(); }
+          }
         }
+      } else {
+        const int k = tk * 128 + warp * 32 + lane;           // row of the [R*S*Cs][Cout] matrix
+        uint32_t tap, c; g.dC.divmod((uint32_t)k, tap, c);
+        const bool row_ok = (int)tap < g.RS && (int)c < g.Cin;
+        float* drow = dw + ((long long)tap * g.Cin + c) * g.Cout;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          uint32_t acc[32];
+          tmem_ld32(tbase + cc * 32, acc);
+          tmem_ld_wait();
+          const int n0 = tn * BN + cc * 32;
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + i < g.Cout) atomicAdd(drow + n0 + i, __uint_as_float(acc[i]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&ctl.tmem_empty[as]);
       }
-      tc_fence_before();
-      mbar_arrive(&ctl.tmem_empty[as]);
       as ^= 1; if (as == 0) aphase ^= 1;
     }
+    if (TMA_RED && threadIdx.x == 0) tma_store_wait_all<0>();
   } else if (warp == 4) {
     Pipe pp{0, 0};
     int as = 0; uint32_t aphase = 0;
@@ -538,36 +574,52 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         }
       }
       const T* src = reinterpret_cast<const T*>(g.src);
+      // The thread's 8 pieces touch only NPX distinct pixels (piece i -> pixel slot i % NPX, atom i / NPX).
+      // Their (n, p, q) coordinates are decoded once per item and then walked forward by PXS per K block.
+      constexpr int NPX = PXS / 16;
+      int sn[NPX], sp[NPX], sq[NPX];
+      long long sm[NPX];
+#pragma unroll
+      for (int e = 0; e < NPX; ++e) {
+        sm[e] = (long long)kb0 * PXS + (gt >> 3) + 16 * e;
+        uint32_t nn, rem, p, qq;
+        g.dPQ.divmod((uint32_t)min(sm[e], (long long)0x7fffffff), nn, rem);
+        g.dQ.divmod(rem, p, qq);
+        sn[e] = (int)nn; sp[e] = (int)p; sq[e] = (int)qq;
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&ctl.empty[pi.stage], pi.phase ^ 1, 80);
         const uint32_t a_addr = smem_u32(smem + (size_t)pi.stage * TL::STAGE_BYTES);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          const int e = i % NPX;
           const int q = (gt >> 3) + 16 * i;
           const int px = q % PXS;
           const uint32_t dst = a_addr + (q / PXS) * ATOM_BYTES + sw128_offset(px, j);
-          const long long m = (long long)kb * PXS + px;
-          int pix = -1, bh = 0, bw = 0;
-          if (m < g.M) {
-            uint32_t nn, rem, p, qq;
-            g.dPQ.divmod((uint32_t)m, nn, rem);
-            g.dQ.divmod(rem, p, qq);
-            pix = (int)nn * g.H * g.W; bh = (int)p * g.stride - g.pad_h; bw = (int)qq * g.stride - g.pad_w;
-          }
+          const bool in_m = sm[e] < g.M;
+          const int pix = sn[e] * g.H * g.W;
+          const int bh = sp[e] * g.stride - g.pad_h, bw = sq[e] * g.stride - g.pad_w;
           if (!SMALLC) {
             const int h = bh + pdr[i], w = bw + pds[i];
-            const bool ok = pk[i] && pix >= 0 && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W;
+            const bool ok = pk[i] && in_m && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W;
             const T* p = src + (long long)(pix + h * g.W + w) * g.C + pc[i];
             cp_async16(dst, ok ? (const void*)p : (const void*)src, ok ? 16u : 0u);
           } else {
             const int h0 = bh + pdr[i], w0 = bw + pds[i], h1 = bh + pdr2[i], w1 = bw + pds2[i];
-            const bool ok0 = pk[i] && pix >= 0 && (unsigned)h0 < (unsigned)g.H && (unsigned)w0 < (unsigned)g.W;
-            const bool ok1 = pk2[i] && pix >= 0 && (unsigned)h1 < (unsigned)g.H && (unsigned)w1 < (unsigned)g.W;
+            const bool ok0 = pk[i] && in_m && (unsigned)h0 < (unsigned)g.H && (unsigned)w0 < (unsigned)g.W;
+            const bool ok1 = pk2[i] && in_m && (unsigned)h1 < (unsigned)g.H && (unsigned)w1 < (unsigned)g.W;
             const T* p0 = src + (long long)(pix + h0 * g.W + w0) * 4;
             const T* p1 = src + (long long)(pix + h1 * g.W + w1) * 4;
             cp_async8(dst, ok0 ? (const void*)p0 : (const void*)src, ok0 ? 8u : 0u);
             cp_async8(dst + 8, ok1 ? (const void*)p1 : (const void*)src, ok1 ? 8u : 0u);
           }
+        }
+#pragma unroll
+        for (int e = 0; e < NPX; ++e) {      // advance the pixel walk by PXS
+          sm[e] += PXS;
+          sq[e] += g.adv_q; sp[e] += g.adv_p;
+          if (sq[e] >= g.Q) { sq[e] -= g.Q; ++sp[e]; }
+          while (sp[e] >= g.P) { sp[e] -= g.P; ++sn[e]; }
         }
         cp_async_commit();
         advance<STAGES>(pi);
@@ -652,6 +704,7 @@ int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, i
   g.H = (int)Hs; g.W = (int)Ws; g.C = (int)Cs; g.R = (int)R; g.S = (int)S; g.RS = (int)(R * S);
   g.stride = (int)stride; g.pad_h = (int)((R - 1) / 2); g.pad_w = (int)((S - 1) / 2);
   g.dPQ = FastDiv((uint32_t)(P * Q)); g.dQ = FastDiv((uint32_t)Q); g.dC = FastDiv((uint32_t)Cs); g.dS = FastDiv((uint32_t)S);
+  g.P = (int)P; g.Q = (int)Q; g.adv_p = g.adv_q = 0;
   g.M = M; g.n_out = (int)n_out; g.ldc = (int)n_out; g.num_kb = (int)(Kp / KBE);
   g.tiles_m = (int)((M + 127) / 128); g.tiles_n = (int)((n_out + bn - 1) / bn);
   g.Cin = g.Cout = 0; g.splits = 1; g.kb_per_split = g.num_kb;
@@ -729,6 +782,7 @@ int run_dgrad_strided(const void* dy, const void* wd, void* dx, int dtype, int o
       g.H = (int)Ho; g.W = (int)Wo; g.C = (int)Cout; g.R = 1; g.S = 1; g.RS = nt;
       g.stride = 1; g.pad_h = 0; g.pad_w = 0;
       g.dPQ = FastDiv((uint32_t)(P2 * Q2)); g.dQ = FastDiv((uint32_t)Q2); g.dC = FastDiv((uint32_t)Cout); g.dS = FastDiv(1);
+      g.P = (int)P2; g.Q = (int)Q2; g.adv_p = g.adv_q = 0;
       g.M = M; g.n_out = (int)Cin; g.ldc = (int)Cin;
       g.cblocks = (int)(Cout / KBE); g.num_kb = nt * g.cblocks;
       g.tiles_m = (int)((M + 127) / 128); g.tiles_n = (int)((Cin + bn - 1) / bn);
@@ -745,29 +799,34 @@ int run_dgrad_strided(const void* dy, const void* wd, void* dx, int dtype, int o
   return SIMCLR_OK;
 }
 
-template <typename T, int BN, bool SMALLC, bool A_TMA>
-int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, const Geom& g, float* dw, cudaStream_t st) {
-  auto kern = wgrad_kernel<T, BN, SMALLC, A_TMA>;
+template <typename T, int BN, bool SMALLC, bool A_TMA, bool TMA_RED>
+int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, const CUtensorMap& tdw, const Geom& g, float* dw,
+                 cudaStream_t st) {
+  auto kern = wgrad_kernel<T, BN, SMALLC, A_TMA, TMA_RED>;
   static bool attr = false;
   if (!attr) { int rc = set_smem_attr(kern, Tile<BN>::SMEM_BYTES); if (rc) return rc; attr = true; }
   int grid = g.tiles_m * g.tiles_n * g.splits; if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, A_TMA ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(tx, tdy, g, dw);
+  kern<<<grid, A_TMA ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(tx, tdy, tdw, g, dw);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
 template <typename T, int BN>
-int dispatch_wgrad2(bool smallc, bool a_tma, const CUtensorMap& tx, const CUtensorMap& tdy, const Geom& g, float* dw,
-                    cudaStream_t st) {
-  if (a_tma) return launch_wgrad<T, BN, false, true>(tx, tdy, g, dw, st);
-  if (smallc) return launch_wgrad<T, BN, true, false>(tx, tdy, g, dw, st);
-  return launch_wgrad<T, BN, false, false>(tx, tdy, g, dw, st);
+int dispatch_wgrad2(bool smallc, bool a_tma, bool tma_red, const CUtensorMap& tx, const CUtensorMap& tdy,
+                    const CUtensorMap& tdw, const Geom& g, float* dw, cudaStream_t st) {
+  if (smallc) return launch_wgrad<T, BN, true, false, false>(tx, tdy, tdw, g, dw, st);
+  if (tma_red) {
+    if (a_tma) return launch_wgrad<T, BN, false, true, true>(tx, tdy, tdw, g, dw, st);
+    return launch_wgrad<T, BN, false, false, true>(tx, tdy, tdw, g, dw, st);
+  }
+  if (a_tma) return launch_wgrad<T, BN, false, true, false>(tx, tdy, tdw, g, dw, st);
+  return launch_wgrad<T, BN, false, false, false>(tx, tdy, tdw, g, dw, st);
 }
 template <typename T>
-int dispatch_wgrad(int bn, bool smallc, bool a_tma, const CUtensorMap& tx, const CUtensorMap& tdy, const Geom& g,
-                   float* dw, cudaStream_t st) {
-  if (bn == 256) return dispatch_wgrad2<T, 256>(smallc, a_tma, tx, tdy, g, dw, st);
-  if (bn == 128) return dispatch_wgrad2<T, 128>(smallc, a_tma, tx, tdy, g, dw, st);
-  return dispatch_wgrad2<T, 64>(smallc, a_tma, tx, tdy, g, dw, st);
+int dispatch_wgrad(int bn, bool smallc, bool a_tma, bool tma_red, const CUtensorMap& tx, const CUtensorMap& tdy,
+                   const CUtensorMap& tdw, const Geom& g, float* dw, cudaStream_t st) {
+  if (bn == 256) return dispatch_wgrad2<T, 256>(smallc, a_tma, tma_red, tx, tdy, tdw, g, dw, st);
+  if (bn == 128) return dispatch_wgrad2<T, 128>(smallc, a_tma, tma_red, tx, tdy, tdw, g, dw, st);
+  return dispatch_wgrad2<T, 64>(smallc, a_tma, tma_red, tx, tdy, tdw, g, dw, st);
 }
 
 }  // namespace
@@ -838,6 +897,7 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   g.H = (int)H; g.W = (int)W; g.C = (int)Cs; g.R = (int)R; g.S = (int)S; g.RS = (int)(R * S);
   g.stride = (int)stride; g.pad_h = (int)((R - 1) / 2); g.pad_w = (int)((S - 1) / 2);
   g.dPQ = FastDiv((uint32_t)(Ho * Wo)); g.dQ = FastDiv((uint32_t)Wo); g.dC = FastDiv((uint32_t)Cs); g.dS = FastDiv((uint32_t)S);
+  g.P = (int)Ho; g.Q = (int)Wo; g.adv_p = pxs / (int)Wo; g.adv_q = pxs % (int)Wo;
   g.M = M; g.n_out = (int)Cout; g.ldc = (int)Cout;
   g.num_kb = (int)((M + pxs - 1) / pxs);
   g.tiles_m = (int)((R * S * Cs + 127) / 128); g.tiles_n = (int)((Cout + bn - 1) / bn);
@@ -856,8 +916,13 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   const bool a_tma = (R == 1 && S == 1 && stride == 1 && !smallc && (Cs * es) % 16 == 0);
   if (a_tma) { rc = make_tmap_2d(&tx, x, es, (uint64_t)M, (uint64_t)Cs, (uint64_t)Cs * es, (uint32_t)pxs, (uint32_t)ATOM_E); if (rc) return rc; }
   else tx = tdy;
+  // splits are combined by TMA reduce-add when dW is a plain [R*S*Cin][Cout] fp32 matrix with 16-byte rows
+  CUtensorMap tdw;
+  const bool tma_red = !smallc && Cs == Cin && aligned16(dw) && (Cout * 4) % 16 == 0;
+  if (tma_red) { rc = make_tmap_2d(&tdw, dw, 4, (uint64_t)(R * S * Cin), (uint64_t)Cout, (uint64_t)Cout * 4, 128, 32); if (rc) return rc; }
+  else tdw = tdy;
   SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(R * S * Cin * Cout) * sizeof(float), st));
-  if (dtype == SIMCLR_BF16) return dispatch_wgrad<__nv_bfloat16>(bn, smallc, a_tma, tx, tdy, g, dw, st);
+  if (dtype == SIMCLR_BF16) return dispatch_wgrad<__nv_bfloat16>(bn, smallc, a_tma, tma_red, tx, tdy, tdw, g, dw, st);
   set_error("conv2d_wgrad_tc: unknown dtype %d", dtype);
   return SIMCLR_ERR_INVALID_ARG;
 }

@@ -57,3 +57,38 @@ def batch_random_blur(images_list, height, width, blur_probability=0.5, draws=No
     tmp = e.empty((T * B, H, W, 3), torch.float32)
     lib.input_prep(x, out, 0, B, H, W, T, 1, height // 10, sigma, selector, tmp, stream_ptr())
     return [out[t * B:(t + 1) * B, :, :, :3] for t in range(T)]
+
+
+def preprocess_for_train_batch(images, draws, height, width, out=None, channel_offset=0):
+    """`preprocess_for_train` (tf2/data_util.py:443-475) for a batch of uint8 images on device.
+
+    images: list of uint8 tensors [Hs,Ws,3] (any device); draws: list of dicts with keys
+    box=(y,x,h,w), flip, color=dict(apply_jitter, perm, brightness, contrast, saturation, hue,
+    apply_gray) -- the reference's tf.random draws.  Returns fp32 [n,height,width,3], or writes
+    into `out` [n,height,width,C] at `channel_offset` (two views -> [B,H,W,6], tf2/data.py:55-58)."""
+    import numpy as np
+    e = get_engine()
+    n = len(images)
+    offs, hw, total = [], [], 0
+    for im in images:
+        assert im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == 3
+        offs.append(total); hw.append([im.shape[0], im.shape[1]]); total += im.numel()
+    src = torch.cat([im.reshape(-1) for im in images]).to(e.device)
+    box = np.asarray([d['box'] for d in draws], dtype=np.int32)
+    for (y, x, h, w), (Hs, Ws) in zip(box, hw):
+        if not (0 <= y and 0 <= x and h > 0 and w > 0 and y + h <= Hs and x + w <= Ws):
+            raise ValueError('crop box out of the image')
+    flip = np.asarray([1 if d['flip'] else 0 for d in draws], dtype=np.uint8)
+    col = np.zeros((n, 8), dtype=np.float32)
+    for i, d in enumerate(draws):
+        c = d['color']
+        code = sum(int(op) << (2 * t) for t, op in enumerate(c['perm']))
+        col[i] = [1.0 if c['apply_jitter'] else 0.0, code, c['brightness'], c['contrast'], c['saturation'], c['hue'],
+                  1.0 if c['apply_gray'] else 0.0, 0.0]
+    t = lambda a: torch.from_numpy(a).to(e.device)
+    if out is None:
+        out = e.empty((n, height, width, 3), torch.float32)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape[:3] == (n, height, width)
+    lib.augment(src, t(np.asarray(offs, dtype=np.int64)), t(np.asarray(hw, dtype=np.int32)), t(box), t(flip), t(col),
+                out, n, height, width, out.shape[3], channel_offset, stream_ptr())
+    return out

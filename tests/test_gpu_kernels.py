@@ -331,3 +331,33 @@ def test_conv_simt(eng, case):
         dx = torch.empty(N, H, W, Cin, device='cuda')
         lib.conv2d_dgrad_simt(dyd, wd_, dx, 0, 0, N, H, W, Cin, Cout, k, k, s, st)
         assert rel_err(dx, xo.grad) < 1e-5
+
+
+# --------------------------------------------------------------------------
+# augmentation (tf2/data_util.py:443-475) with injected draws
+# --------------------------------------------------------------------------
+def test_augment_matches_oracle(eng):
+    from oracle import data_util as OD
+    from simclr_b200 import data_util as D
+    g = torch.Generator().manual_seed(3)
+    H = W = 64
+    images, draws = [], []
+    perms = [(0, 1, 2, 3), (3, 2, 1, 0), (1, 0, 3, 2), (2, 3, 0, 1), (0, 2, 1, 3), (1, 3, 0, 2)]
+    for i in range(6):
+        Hs, Ws = 70 + 13 * i, 90 + 7 * i
+        images.append(torch.randint(0, 256, (Hs, Ws, 3), dtype=torch.uint8, generator=g))
+        h, w = 30 + 5 * i, 40 + 3 * i
+        draws.append(dict(box=(3 + i, 2 * i, h, w), flip=bool(i % 2),
+                          color=dict(apply_jitter=(i != 4), perm=perms[i], brightness=0.6 + 0.15 * i, contrast=0.5 + 0.2 * i,
+                                     saturation=0.4 + 0.25 * i, hue=-0.2 + 0.07 * i, apply_gray=(i == 2 or i == 5))))
+    images.append(images[0][:40, :50].contiguous())        # upscaling crop that touches the image border
+    draws.append(dict(box=(0, 0, 40, 50), flip=False, color=dict(apply_jitter=False, perm=perms[0], brightness=1., contrast=1.,
+                                                                   saturation=1., hue=0., apply_gray=False)))
+    ref = torch.stack([OD.preprocess_for_train(im.double() / 255.0, H, W, d) for im, d in zip(images, draws)])
+    out = D.preprocess_for_train_batch(images, draws, H, W)
+    assert out.shape == (7, H, W, 3)
+    assert (out.cpu().double() - ref).abs().max() < 2e-5
+    # two views written straight into the 6-channel feature tensor
+    feat = torch.zeros(7, H, W, 6, device='cuda')
+    D.preprocess_for_train_batch(images, draws, H, W, out=feat, channel_offset=3)
+    assert torch.equal(feat[..., 3:], out) and torch.count_nonzero(feat[..., :3]) == 0
