@@ -212,6 +212,29 @@ SIMCLR_API int simclr_conv2d_wgrad_simt(const void* x, const void* dy, float* dw
                                         int64_t R, int64_t S, int64_t stride, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Selective-kernel block (tf2/resnet.py:217-277 SK_Conv2D) and ResNet-D shortcut
+ * pooling (tf2/resnet.py:333-340,401-408).  x is the BN+ReLU output of the 3x3 conv,
+ * [N][HW][2f]; stream s occupies channels [s*f, (s+1)*f).
+ * ------------------------------------------------------------------------- */
+/* g[n,c] = mean_hw(x[n,hw,c] + x[n,hw,f+c])                       (tf2/resnet.py:265-266) */
+SIMCLR_API int simclr_sk_pool(const void* x, int dtype, float* g, int64_t N, int64_t HW, int64_t f, void* stream);
+/* mixing = softmax over the two streams of logits [N][2f]; out[n,hw,c] = x0*m0 + x1*m1  (:270-275) */
+SIMCLR_API int simclr_sk_mix_fwd(const void* x, const float* logits, float* mixing, void* out, int dtype,
+                                 int64_t N, int64_t HW, int64_t f, void* stream);
+/* dlogits [N][2f] = softmax backward of dmix_s[n,c] = sum_hw dout*x_s */
+SIMCLR_API int simclr_sk_mix_bwd_reduce(const void* dout, const void* x, const float* mixing, float* dlogits,
+                                        int dtype, int64_t N, int64_t HW, int64_t f, void* stream);
+/* dx[n,hw,s*f+c] = dout[n,hw,c]*m_s[n,c] + dg[n,c]/HW  (dg: gradient w.r.t. the pooled features) */
+SIMCLR_API int simclr_sk_mix_bwd_apply(const void* dout, const float* mixing, const float* dg, void* dx, int dtype,
+                                       int64_t N, int64_t HW, int64_t f, void* stream);
+/* AveragePooling2D(2, stride): stride 2 = FixedPadding(2) + 'VALID'; stride 1 = 'SAME' with the
+ * divisor counting valid elements only.  x [N,H,W,C]. */
+SIMCLR_API int simclr_avgpool2x2_fwd(const void* x, void* y, int dtype, int64_t N, int64_t H, int64_t W, int64_t C,
+                                     int64_t stride, void* stream);
+SIMCLR_API int simclr_avgpool2x2_bwd(const void* dy, void* dx, int dtype, int64_t N, int64_t H, int64_t W,
+                                     int64_t C, int64_t stride, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Input preparation: split views, batch_random_blur, cast, pad 3->4 channels
  * (tf2/model.py:250-259, tf2/data_util.py:323-361,393-440)
  *   features [B,H,W,3*T] fp32 in [0,1]  ->  out [T*B,H,W,4] (view-major)

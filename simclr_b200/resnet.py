@@ -7,8 +7,8 @@ Class names, constructor arguments and the `resnet()` factory mirror
 `backward(grad)`.  Activations are NHWC torch tensors in the engine's activation
 dtype; variables are fp32 HWIO / [C] views into flat buffers.
 
-Not yet on the GPU path (raise at construction): SK (`sk_ratio > 0`) and SE
-(`se_ratio > 0`) blocks.
+SK blocks (`sk_ratio > 0`, with the ResNet-D stem and shortcuts, config 5) are
+on the GPU path; SE (`se_ratio > 0`, in no BASELINE config) raises at construction.
 """
 import torch
 
@@ -199,17 +199,106 @@ class Conv2dFixedPadding:  # pylint: disable=missing-docstring
 
 
 class _Shortcut:
-    """Projection shortcut: Conv1x1(stride) + BN without ReLU (tf2/resnet.py:342-353,415-423)."""
+    """Projection shortcut: Conv1x1(stride) + BN without ReLU (tf2/resnet.py:342-353,415-423);
+    with SK the ResNet-D form: [FixedPadding(2)] AveragePooling2D(2, stride) + Conv1x1(1) + BN
+    (tf2/resnet.py:331-341,401-414)."""
 
     def __init__(self, vs, scope, cin, filters_out, strides):
-        self.conv = Conv2dFixedPadding(vs, scope, cin, filters_out, 1, strides)
+        self.resnet_d = FLAGS.sk_ratio > 0
+        self.strides = strides
+        self.conv = Conv2dFixedPadding(vs, scope, cin, filters_out, 1, 1 if self.resnet_d else strides)
         self.bn = BatchNormRelu(vs, scope, filters_out, relu=False)
+        self.in_shape = None
 
     def __call__(self, x, training):
+        if self.resnet_d:
+            e = get_engine()
+            N, H, W, C = x.shape
+            s = self.strides
+            Ho, Wo = (H, W) if s == 1 else ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
+            y = e.empty((N, Ho, Wo, C), x.dtype)
+            lib.avgpool2x2_fwd(x, y, e.code(x.dtype), N, H, W, C, s, stream_ptr())
+            self.in_shape = (N, H, W, C)
+            x = y
         return self.bn(self.conv(x, training), training)
 
     def backward(self, d):
-        return self.conv.backward(self.bn.backward(d))
+        d = self.conv.backward(self.bn.backward(d))
+        if self.resnet_d:
+            e = get_engine()
+            N, H, W, C = self.in_shape
+            dx = e.empty((N, H, W, C), d.dtype)
+            lib.avgpool2x2_bwd(d, dx, e.code(d.dtype), N, H, W, C, self.strides, stream_ptr())
+            d = dx
+        return d
+
+
+class SK_Conv2D:  # pylint: disable=invalid-name
+    """Selective kernel convolutional layer (tf2/resnet.py:217-277)."""
+
+    def __init__(self, vs, scope, cin, filters, strides, sk_ratio, min_dim=32):
+        from . import model as model_lib       # the two mixing "convs" are dense layers on [N, f]
+        scope = scope + '/' + vs.namer('sk_conv2d')
+        self.filters = filters
+        # Two stream convs (using split and both are 3x3).
+        self.conv2d_fixed_padding = Conv2dFixedPadding(vs, scope, cin, 2 * filters, 3, strides)
+        self.batch_norm_relu = BatchNormRelu(vs, scope, 2 * filters)
+        # Mixing weights for two streams.
+        mid_dim = max(int(filters * sk_ratio), min_dim)
+        self.mid_dim = mid_dim
+        c0 = vs.namer('conv2d')
+        self.kernel0 = vs.add('%s/%s/kernel:0' % (scope, c0), (1, 1, filters, mid_dim), 'variance_scaling')
+        self.conv2d_0 = ConvOp(self.kernel0, 1, 1, filters, mid_dim, 1)
+        self.batch_norm_relu_1 = BatchNormRelu(vs, scope, mid_dim)
+        c1 = vs.namer('conv2d')
+        self.kernel1 = vs.add('%s/%s/kernel:0' % (scope, c1), (1, 1, mid_dim, 2 * filters), 'variance_scaling')
+        self.conv2d_1 = ConvOp(self.kernel1, 1, 1, mid_dim, 2 * filters, 1)
+        self.saved = None
+
+    def __call__(self, inputs, training):
+        e = get_engine()
+        st = stream_ptr()
+        f = self.filters
+        x = self.batch_norm_relu(self.conv2d_fixed_padding(inputs, training), training)     # [N,H,W,2f]
+        N, H, W, _ = x.shape
+        HW = H * W
+        g32 = e.empty((N, f), torch.float32)
+        lib.sk_pool(x, e.code(x.dtype), g32, N, HW, f, st)                                  # mean of the stream sum
+        g = g32 if e.act_dtype == torch.float32 else self._cast(g32, e.act_dtype)
+        h = self.conv2d_0.forward(g.view(N, 1, 1, f), training).view(N, self.mid_dim)
+        h = self.batch_norm_relu_1(h, training)
+        logits = self.conv2d_1.forward(h.view(N, 1, 1, self.mid_dim), training, out_dtype=torch.float32).view(N, 2 * f)
+        mixing = e.empty((N, 2 * f), torch.float32)
+        out = e.empty((N, H, W, f), x.dtype)
+        lib.sk_mix_fwd(x, logits, mixing, out, e.code(x.dtype), N, HW, f, st)
+        if training:
+            self.saved = (x, mixing, (N, H, W))
+        return out
+
+    @staticmethod
+    def _cast(t, dtype):
+        e = get_engine()
+        o = e.empty(t.shape, dtype)
+        lib.cast(t, e.code(t.dtype), o, e.code(dtype), t.numel(), stream_ptr())
+        return o
+
+    def backward(self, dout):
+        e = get_engine()
+        st = stream_ptr()
+        x, mixing, (N, H, W) = self.saved
+        self.saved = None
+        f, HW = self.filters, H * W
+        dlogits = e.empty((N, 2 * f), torch.float32)
+        lib.sk_mix_bwd_reduce(dout, x, mixing, dlogits, e.code(dout.dtype), N, HW, f, st)
+        dl = dlogits if e.act_dtype == torch.float32 else self._cast(dlogits, e.act_dtype)
+        dh = self.conv2d_1.backward(dl.view(N, 1, 1, 2 * f)).view(N, self.mid_dim)
+        dh = self.batch_norm_relu_1.backward(dh)
+        dg = self.conv2d_0.backward(dh.view(N, 1, 1, self.mid_dim)).view(N, f)
+        dg32 = dg if dg.dtype == torch.float32 else self._cast(dg, torch.float32)
+        dx = e.empty(x.shape, x.dtype)
+        lib.sk_mix_bwd_apply(dout, mixing, dg32, dx, e.code(dout.dtype), N, HW, f, st)
+        d = self.batch_norm_relu.backward(dx)
+        return self.conv2d_fixed_padding.backward(d)
 
 
 class ResidualBlock:  # pylint: disable=missing-docstring
@@ -247,8 +336,12 @@ class BottleneckBlock:
         self.shortcut = _Shortcut(vs, scope, cin, 4 * filters, strides) if use_projection else None
         self.c1 = Conv2dFixedPadding(vs, scope, cin, filters, 1, 1)
         self.b1 = BatchNormRelu(vs, scope, filters)
-        self.c2 = Conv2dFixedPadding(vs, scope, filters, filters, 3, strides)
-        self.b2 = BatchNormRelu(vs, scope, filters)
+        if FLAGS.sk_ratio > 0:
+            self.sk = SK_Conv2D(vs, scope, filters, filters, strides, FLAGS.sk_ratio)
+        else:
+            self.sk = None
+            self.c2 = Conv2dFixedPadding(vs, scope, filters, filters, 3, strides)
+            self.b2 = BatchNormRelu(vs, scope, filters)
         self.c3 = Conv2dFixedPadding(vs, scope, filters, 4 * filters, 1, 1)
         self.b3 = BatchNormRelu(vs, scope, 4 * filters, relu=False, init_zero=True)
         self.cout = 4 * filters
@@ -256,15 +349,18 @@ class BottleneckBlock:
     def __call__(self, inputs, training):
         shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
         x = self.b1(self.c1(inputs, training), training)
-        x = self.b2(self.c2(x, training), training)
+        x = self.sk(x, training) if self.sk is not None else self.b2(self.c2(x, training), training)
         x = self.c3(x, training)
         return self.b3(x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :487
 
     def backward(self, d_out, d_out2=None):
         dy = self.b3.backward(d_out, d_out2)
         d = self.c3.backward(dy)
-        d = self.b2.backward(d)
-        d = self.c2.backward(d)
+        if self.sk is not None:
+            d = self.sk.backward(d)
+        else:
+            d = self.b2.backward(d)
+            d = self.c2.backward(d)
         d = self.b1.backward(d)
         dx_a = self.c1.backward(d)
         dx_b = d_out if self.shortcut is None else self.shortcut.backward(d_out)
@@ -300,16 +396,26 @@ class Resnet:  # pylint: disable=missing-docstring
     STEM_CS = 4
 
     def __init__(self, vs, block_fn, layers, width_multiplier, cifar_stem=False):
-        if FLAGS.sk_ratio > 0 or FLAGS.se_ratio > 0:
-            raise NotImplementedError('SK / SE blocks are not on the B200 path yet (sk_ratio/se_ratio must be 0)')
+        if FLAGS.se_ratio > 0:
+            raise NotImplementedError('SE blocks are not on the B200 path yet (se_ratio must be 0)')
         scope = 'resnet'
         wm = width_multiplier
         self.cifar_stem = cifar_stem
+        self.stem_extra = []          # ResNet-D: two more conv+BN pairs after the first
         if cifar_stem:                                            # :551-564
             self.stem_conv = Conv2dFixedPadding(vs, scope, 3, 64 * wm, 3, 1, stored_cin=self.STEM_CS, need_dgrad=False)
+            self.stem_bn = BatchNormRelu(vs, scope, 64 * wm)
+        elif FLAGS.sk_ratio > 0:                                  # ResNet-D stem :566-591
+            self.stem_conv = Conv2dFixedPadding(vs, scope, 3, 64 * wm // 2, 3, 2, stored_cin=self.STEM_CS, need_dgrad=False)
+            self.stem_bn = BatchNormRelu(vs, scope, 64 * wm // 2)
+            c2 = Conv2dFixedPadding(vs, scope, 64 * wm // 2, 64 * wm // 2, 3, 1)
+            b2 = BatchNormRelu(vs, scope, 64 * wm // 2)
+            c3 = Conv2dFixedPadding(vs, scope, 64 * wm // 2, 64 * wm, 3, 1)
+            b3 = BatchNormRelu(vs, scope, 64 * wm)
+            self.stem_extra = [(c2, b2), (c3, b3)]
         else:                                                     # :593-604
             self.stem_conv = Conv2dFixedPadding(vs, scope, 3, 64 * wm, 7, 2, stored_cin=self.STEM_CS, need_dgrad=False)
-        self.stem_bn = BatchNormRelu(vs, scope, 64 * wm)
+            self.stem_bn = BatchNormRelu(vs, scope, 64 * wm)
         self.block_groups = []
         cin = 64 * wm
         for i, (f, s) in enumerate(zip([64, 128, 256, 512], [1, 2, 2, 2])):
@@ -326,6 +432,8 @@ class Resnet:  # pylint: disable=missing-docstring
         if endpoints is not None:
             endpoints['initial_conv'] = x
         x = self.stem_bn(x, training)
+        for conv, bn in self.stem_extra:
+            x = bn(conv(x, training), training)
         pool_saved = None
         if not self.cifar_stem:                                   # MaxPooling2D(3, 2, 'SAME'), :605-611
             N, H, W, C = x.shape
@@ -366,6 +474,9 @@ class Resnet:  # pylint: disable=missing-docstring
             dx = e.empty((N, H, W, C))
             lib.maxpool3x3s2_bwd(d, argmax, dx, e.code(d.dtype), N, H, W, C, st)
             d, d2 = dx, None
+        for conv, bn in reversed(self.stem_extra):
+            d = conv.backward(bn.backward(d, d2))
+            d2 = None
         dy = self.stem_bn.backward(d, d2)
         self.stem_conv.backward(dy, need_dx=False)
 

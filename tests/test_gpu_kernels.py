@@ -361,3 +361,57 @@ def test_augment_matches_oracle(eng):
     feat = torch.zeros(7, H, W, 6, device='cuda')
     D.preprocess_for_train_batch(images, draws, H, W, out=feat, channel_offset=3)
     assert torch.equal(feat[..., 3:], out) and torch.count_nonzero(feat[..., :3]) == 0
+
+
+# --------------------------------------------------------------------------
+# SK block pieces and ResNet-D pooling (tf2/resnet.py:217-277, 333-340, 401-408)
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize('H,W,stride', [(8, 8, 2), (7, 9, 2), (6, 6, 1), (5, 7, 1)])
+def test_avgpool2x2(eng, H, W, stride):
+    from oracle import resnet as OR
+    from simclr_b200._lib import lib, stream_ptr
+    torch.manual_seed(H * W + stride)
+    N, C = 3, 16
+    x = torch.randn(N, H, W, C)
+    xo = x.double().requires_grad_(True)
+    yo = OR.avg_pool_2x2(xo.permute(0, 3, 1, 2), stride).permute(0, 2, 3, 1)
+    dy = torch.randn(yo.shape)
+    yo.backward(dy.double())
+    y = torch.empty(yo.shape, device='cuda')
+    lib.avgpool2x2_fwd(_dev(x), y, 0, N, H, W, C, stride, stream_ptr())
+    assert rel_err(y, yo) < 1e-6
+    dx = torch.empty(N, H, W, C, device='cuda')
+    lib.avgpool2x2_bwd(_dev(dy), dx, 0, N, H, W, C, stride, stream_ptr())
+    assert rel_err(dx, xo.grad) < 1e-6
+
+
+@pytest.mark.parametrize('strides', [1, 2])
+def test_sk_conv2d_fwd_bwd(eng, flags, strides):
+    """The whole SK_Conv2D layer (conv, BN, pooled mixing MLP, softmax mix) vs the oracle."""
+    from oracle import resnet as OR
+    from oracle.config import default_cfg
+    from simclr_b200 import resnet as R
+    from simclr_b200.engine import VarStore
+    flags.set_flags(sk_ratio=0.0625)
+    torch.manual_seed(10 + strides)
+    N, H, W, cin, f = 6, 8, 8, 16, 32
+    vs = VarStore()
+    sk = R.SK_Conv2D(vs, 's', cin, f, strides, 0.0625)
+    vs.materialize(eng.device, seed=3)
+    cfg = default_cfg(sk_ratio=0.0625)
+    ovs = OR.VarStore()
+    osk = OR.SK_Conv2D(ovs, cfg, 's', cin, f, strides, 0.0625)
+    assert [v.name for v in vs.trainable] == list(ovs.trainable)
+    P = {v.name: v.value.detach().cpu().double().requires_grad_(True) for v in vs.trainable}
+    S = {v.name: v.value.detach().cpu().double() for v in vs.moving}
+    x = torch.randn(N, H, W, cin)
+    xo = x.double().requires_grad_(True)
+    yo = osk(P, S, xo.permute(0, 3, 1, 2), True).permute(0, 2, 3, 1)
+    dy = torch.randn(yo.shape)
+    yo.backward(dy.double())
+    y = sk(_dev(x), True)
+    assert rel_err(y, yo) < 1e-5
+    dx = sk.backward(_dev(dy))
+    assert rel_err(dx, xo.grad) < 1e-4
+    for v in vs.trainable:
+        assert rel_err(v.grad, P[v.name].grad) < 2e-4, v.name

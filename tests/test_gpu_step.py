@@ -156,3 +156,33 @@ def test_two_steps_graph_replay(flags):
         torch.cuda.synchronize()
         results.append(trainer.model.vs.flat_value.clone())
     assert rel_err(results[1], results[0]) < 2e-3     # atomics in wgrad/BN make it non-bitwise
+
+
+def test_step_parity_sk_resnet_d(flags):
+    """Config-5 family: SK blocks with the ResNet-D stem/shortcuts (ResNet-50 SK, reduced to
+    64x64 / batch 8 so the oracle finishes in seconds), fp32 verification mode."""
+    from oracle import step as OS
+    from simclr_b200 import flags_def
+    B, S = 8, 64
+    flags_def.set_flags(sk_ratio=0.0625)
+    trainer, om, P, S_ = _setup(flags, 'fp32', 'simt', False, B, S, depth=50, use_blur=False)
+    f, lab, _, _ = _data(B, S)
+    info = OS.forward_backward(om, P, S_, [f], [lab])
+    P64 = collections.OrderedDict((k, v.double()) for k, v in P.items())
+    S64 = collections.OrderedDict((k, v.double()) for k, v in S_.items())
+    i64 = OS.forward_backward(om, P64, S64, [f.double()], [lab.double()])
+    trainer.optimizer.learning_rate = 0.0
+    loss = trainer.single_step(f.cuda(), lab.cuda())
+    torch.cuda.synchronize()
+    assert abs(loss.item() - i64['loss'].item()) < 1e-4 * abs(i64['loss'].item())
+    worst = 0.0
+    for v in trainer.model.trainable_variables:
+        ref = i64['grads'][v.name]
+        err = rel_err(v.grad, ref)
+        if ref.norm() == 0:
+            assert err < 1e-6, (v.name, err)
+        else:
+            tol = max(1e-3, 5 * rel_err(info['grads'][v.name], ref))
+            assert err < tol, (v.name, err)
+            worst = max(worst, err)
+    print('SK worst grad rel err', worst)
