@@ -158,7 +158,14 @@ def run_b200(args):
     from simclr_b200 import engine, run, flags_def
     from simclr_b200._lib import lib
 
+    t_start = time.time()
+
+    def log(msg):
+        sys.stderr.write('[bench rank %s +%.1fs] %s\n' % (os.environ.get('RANK', '0'), time.time() - t_start, msg))
+        sys.stderr.flush()
+
     rank = run.init_distributed()
+    log('process group ready')
     world = dist.get_world_size() if dist.is_initialized() else 1
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
@@ -175,8 +182,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    log('model built')
     # ---- capture -------------------------------------------------------------
-    use_graph = not args.no_graph
+    # One CUDA graph per step on a single GPU.  With more than one rank the step is launched eagerly
+    # (NCCL collectives between the kernels): the ~700 launches per step cost a few ms of host time
+    # that hide behind a ~100 ms GPU step.
+    use_graph = (not args.no_graph) and world == 1
     launches0 = lib.launch_count
     if use_graph:
         trainer.capture(features, labels, warmup=1)
@@ -192,9 +203,11 @@ def run_b200(args):
         step_fn()
         launches_per_step = lib.launch_count - c0
 
+    log('first step / capture done')
     for _ in range(max(args.warmup, 3)):
         step_fn()
     barrier()
+    log('warm-up done')
 
     # ---- timed region: K steps, inputs resident in HBM -----------------------
     sampler = ClockSampler(local) if rank == 0 else None
@@ -220,6 +233,7 @@ def run_b200(args):
     ips = B * world * args.steps / (ms / 1e3)
     loss_val = float(loss)
 
+    log('timed region done: %.2f ms/step' % ms_per_step)
     # ---- e2e: host buffers, H2D inside the timed region, D2H of the loss ------
     host_f = [torch.rand(B, S, S, 6).pin_memory() for _ in range(2)]
     host_l = [labels.cpu().pin_memory() for _ in range(2)]
@@ -267,18 +281,19 @@ def run_b200(args):
     e2e_ips = B * world * e2e_steps / (float(t.item()) / 1e3)
     h2d_bytes = features.numel() * 4 + labels.numel() * 4
 
+    log('e2e done')
     # ---- roofline pass: per-launch CUDA-event timing of the tcgen05 kernels ----
     roof = None
+    # every rank runs the profiled step (it contains collectives); rank 0 reports its own timings
+    eng.profile = []
+    trainer.single_step(features, labels)
+    torch.cuda.synchronize()
     if rank == 0:
         peaks = measured_peaks()
-        eng.profile = []
-        trainer.single_step(features, labels)
-        torch.cuda.synchronize()
         by = {}
         for kind, shape, flops, a, b in eng.profile:
             d = by.setdefault(kind, [0.0, 0.0, 0])
             d[0] += flops; d[1] += a.elapsed_time(b) * 1e-3; d[2] += 1
-        eng.profile = None
         tot_f = sum(v[0] for v in by.values()); tot_t = sum(v[1] for v in by.values())
         achieved = tot_f / tot_t / 1e12 if tot_t > 0 else 0.0
         key = (args.resnet_depth, args.width_multiplier, S)
@@ -286,12 +301,14 @@ def run_b200(args):
         roof = {'bound': 'tensor', 'kernel': 'igemm_kernel/wgrad_kernel (tcgen05 implicit GEMM, %d launches/step)' % sum(v[2] for v in by.values()),
                 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops'],
                 'traffic': None, 'peak_source': peaks['which'],
-                'conv_share_of_step': tot_t * 1e3 / ms_per_step if not use_graph else None,
+                'conv_share_of_step': tot_t * 1e3 / ms_per_step,
                 'conv_kernel_ms': tot_t * 1e3,
                 'by_kind': {k: {'tflops': v[0] / v[1] / 1e12, 'ms': v[1] * 1e3, 'launches': v[2]} for k, v in by.items()},
                 'whole_step_tflops': step_tflops,
                 'whole_step_frac': None if step_tflops is None else step_tflops / peaks['tflops']}
 
+    eng.profile = None
+    log('profile pass done')
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -321,8 +338,20 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def _watchdog(seconds):
+    """Abort (instead of hanging a whole GPU box) if the run does not finish in time."""
+    import signal
+
+    def handler(signum, frame):
+        sys.stderr.write('bench.py: watchdog expired after %d s\n' % seconds)
+        os._exit(3)
+    signal.signal(signal.SIGALRM, handler)
+    signal.alarm(seconds)
+
+
 def main():
     args = parse_args()
+    _watchdog(int(os.environ.get('SIMCLR_BENCH_TIMEOUT', '900')))
     if args.impl == 'reference':
         run_reference(args)
     else:

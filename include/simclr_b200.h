@@ -188,9 +188,11 @@ SIMCLR_API int simclr_global_avgpool_bwd(const void* dy, int dy_dtype, void* dx,
 SIMCLR_API int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, int64_t R,
                                        int64_t S, int64_t Cin, int64_t Cs, int64_t Cout, int64_t Kp,
                                        void* stream);
+/* bn_sums (nullable): [2][Cout] doubles receiving sum y / sum y^2 of the stored outputs -- the
+ * BatchNorm statistics of tf2/resnet.py:50-72 fused into the conv epilogue (zeroed by the call). */
 SIMCLR_API int simclr_conv2d_fprop_tc(const void* x, const void* wf, void* y, int dtype, int y_dtype,
                                       int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cout, int64_t R,
-                                      int64_t S, int64_t stride, void* stream);
+                                      int64_t S, int64_t stride, double* bn_sums, void* stream);
 SIMCLR_API int simclr_conv2d_dgrad_tc(const void* dy, const void* wd, void* dx, int dtype, int dx_dtype,
                                       int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t R,
                                       int64_t S, int64_t stride, void* stream);

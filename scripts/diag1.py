@@ -50,13 +50,13 @@ def tf32_probe():
             wf, wd = _pack(w, dtype, k, Cin, Cin, Cout)
             y = torch.full((N, H, W, Cout), float('nan'), device='cuda')
             code = 0 if dtype == torch.float32 else 1
-            lib.conv2d_fprop_tc(x.cuda(), wf, y, code, 0, N, H, W, Cin, Cout, k, k, s, stream_ptr())
+            lib.conv2d_fprop_tc(x.cuda(), wf, y, code, 0, N, H, W, Cin, Cout, k, k, s, None, stream_ptr())
             torch.cuda.synchronize()
             print('tf32 probe', dtype, (N, H, W, Cin, Cout, k, s), 'y[0,5,5,:4]', y[0, 5, 5, :4].tolist(), 'expect', 0.5 * Cin * k * k,
                   'wf[0,:4]', wf[0, :4].tolist(), 'nan count', int(torch.isnan(y).sum()))
             xr = torch.randn(N, H, W, Cin).to(dtype); wr = (torch.randn(k, k, Cin, Cout) * 0.1).to(dtype)
             wf, wd = _pack(wr, dtype, k, Cin, Cin, Cout)
-            lib.conv2d_fprop_tc(xr.cuda(), wf, y, code, 0, N, H, W, Cin, Cout, k, k, s, stream_ptr())
+            lib.conv2d_fprop_tc(xr.cuda(), wf, y, code, 0, N, H, W, Cin, Cout, k, k, s, None, stream_ptr())
             torch.cuda.synchronize()
             print('   random rel err', rel_err(y, conv_reference(xr.double(), wr.double(), k, s)))
 

@@ -20,6 +20,7 @@ ap.add_argument('--only', default='fprop,dgrad,wgrad')
 ap.add_argument('--reps', type=int, default=3)
 ap.add_argument('--out', default=None)
 ap.add_argument('--layers', default=None, help='comma separated indices into the shape list')
+ap.add_argument('--fused_stats', action='store_true', help='fprop with BN statistics fused into the epilogue')
 args = ap.parse_args()
 kinds = args.only.split(',')
 sel = range(len(R50)) if args.layers is None else [int(i) for i in args.layers.split(',')]
@@ -42,9 +43,10 @@ for idx in sel:
     y = torch.empty(N, Ho, Ho, Cout, dtype=torch.bfloat16, device='cuda')
     dx = torch.empty(N, H, H, Cin, dtype=torch.bfloat16, device='cuda')
     dw = torch.empty(k, k, Cin, Cout, device='cuda')
+    sums = torch.empty(2 * Cout, dtype=torch.float64, device='cuda')
     M = N * Ho * Ho
     flops = 2.0 * M * k * k * Cin * Cout
-    ops = {'fprop': lambda: lib.conv2d_fprop_tc(x, wf, y, 1, 1, N, H, H, Cs, Cout, k, k, s, st),
+    ops = {'fprop': lambda: lib.conv2d_fprop_tc(x, wf, y, 1, 1, N, H, H, Cs, Cout, k, k, s, sums if args.fused_stats else None, st),
            'dgrad': (lambda: lib.conv2d_dgrad_tc(dy, wd, dx, 1, 1, N, H, H, Cin, Cout, k, k, s, st)) if wd is not None else None,
            'wgrad': lambda: lib.conv2d_wgrad_tc(x, dy, dw, 1, N, H, H, Cs, Cin, Cout, k, k, s, st)}
     minbytes = {'fprop': (x.numel() + y.numel()) * 2, 'dgrad': (dy.numel() + dx.numel()) * 2, 'wgrad': (x.numel() + dy.numel()) * 2}

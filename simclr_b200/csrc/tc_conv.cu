@@ -131,10 +131,10 @@ __device__ __forceinline__ SmemCtl carve(uint8_t* base, int stage_bytes) {
 // ===========================================================================
 // fprop / dgrad / dense:  out[M][n_out] = gather(src)[M][K] * Wk[n_out][K]^T
 // ===========================================================================
-template <typename T, typename To, int BN, bool A_TMA, bool SMALLC, bool TMA_EPI>
+template <typename T, typename To, int BN, bool A_TMA, bool SMALLC, bool TMA_EPI, bool STATS>
 __global__ void __launch_bounds__(A_TMA ? 192 : 320, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-             const __grid_constant__ CUtensorMap tmap_out, const Geom g) {
+             const __grid_constant__ CUtensorMap tmap_out, const Geom g, double* __restrict__ bn_sums) {
   using TL = Tile<BN>;
   constexpr int STAGES = TL::STAGES;
   constexpr bool TF32 = Elt<T>::TF32;
@@ -179,6 +179,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       constexpr int BOXES = BN / BOX_COLS;
       uint32_t box_ctr = 0;
       const int row = warp * 32 + lane;
+      // fused BatchNorm statistics (tf2/resnet.py:50-72): per-column sum / sum of squares of the
+      // *stored* (rounded) outputs, accumulated in registers over all tiles of this CTA (the host
+      // makes gridDim a multiple of tiles_n so a CTA keeps one column block) and flushed once.
+      // Thread t owns 16-byte chunk (t & 7) -- CPC consecutive columns -- of rows (t >> 3)*8 .. +7 of
+      // every staged tile: 8 conflict-free LDS.128 per box, partial sums kept in registers.
+      constexpr int CPC = 16 / (int)sizeof(To);             // columns per chunk: 8 (bf16) / 4 (fp32)
+      const int sj = threadIdx.x & 7, srg = threadIdx.x >> 3;
+      float st_sum[BOXES][CPC], st_sq[BOXES][CPC];
+#pragma unroll
+      for (int b = 0; b < BOXES; ++b)
+#pragma unroll
+        for (int c = 0; c < CPC; ++c) { st_sum[b][c] = 0.f; st_sq[b][c] = 0.f; }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / g.tiles_n, tn = tile - tm * g.tiles_n;
         mbar_wait(&ctl.tmem_full[as], aphase, 10);
@@ -223,9 +235,52 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             fence_proxy_async();
             named_barrier_sync(1, EPI_THREADS);
             if (threadIdx.x == 0) { tma_store_2d(&tmap_out, stage, n0, tm * 128); tma_store_commit(); }
+            if (STATS) {
+              float a0[CPC], a1[CPC];
+#pragma unroll
+              for (int c = 0; c < CPC; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {                 // rows srg*8 + i (rows >= M hold exact zeros)
+                const uint4 raw = *reinterpret_cast<const uint4*>(stage + (srg * 8 + i) * 128 + ((sj ^ i) << 4));
+                float v[CPC];
+                if (sizeof(To) == 2) {
+                  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) { v[(2 * e) % CPC] = __uint_as_float(w[e] << 16); v[(2 * e + 1) % CPC] = __uint_as_float(w[e] & 0xffff0000u); }
+                } else {
+                  v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2 % CPC] = __uint_as_float(raw.z); v[3 % CPC] = __uint_as_float(raw.w);
+                }
+#pragma unroll
+                for (int c = 0; c < CPC; ++c) { a0[c] += v[c]; a1[c] = fmaf(v[c], v[c], a1[c]); }
+              }
+#pragma unroll
+              for (int bb = 0; bb < BOXES; ++bb)
+                if (bb == b) {
+#pragma unroll
+                  for (int c = 0; c < CPC; ++c) { st_sum[bb][c] += a0[c]; st_sq[bb][c] += a1[c]; }
+                }
+            }
           }
         }
         as ^= 1; if (as == 0) aphase ^= 1;
+      }
+      if (STATS) {
+        const int tn0 = blockIdx.x % g.tiles_n;            // constant for this CTA (gridDim % tiles_n == 0)
+#pragma unroll
+        for (int b = 0; b < BOXES; ++b) {
+#pragma unroll
+          for (int c = 0; c < CPC; ++c) {
+            // fold the 4 row groups of the warp (lane >> 3) onto lanes 0-7
+            float s0 = st_sum[b][c], s1 = st_sq[b][c];
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            const int col = tn0 * BN + b * BOX_COLS + sj * CPC + c;
+            if (lane < 8 && col < g.n_out && (int)blockIdx.x < num_tiles) {
+              atomicAdd(bn_sums + col, (double)s0);
+              atomicAdd(bn_sums + g.n_out + col, (double)s1);
+            }
+          }
+        }
       }
       if (threadIdx.x == 0) tma_store_wait_all<0>();
     } else {
@@ -653,42 +708,49 @@ template <typename K> int set_smem_attr(K kernel, size_t bytes) {
   return SIMCLR_OK;
 }
 
-template <typename T, typename To, int BN, bool A_TMA, bool SMALLC, bool TMA_EPI>
-int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const Geom& g, cudaStream_t st) {
-  auto kern = igemm_kernel<T, To, BN, A_TMA, SMALLC, TMA_EPI>;
+template <typename T, typename To, int BN, bool A_TMA, bool SMALLC, bool TMA_EPI, bool STATS>
+int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const Geom& g, double* bn_sums,
+                 cudaStream_t st) {
+  auto kern = igemm_kernel<T, To, BN, A_TMA, SMALLC, TMA_EPI, STATS>;
   static bool attr = false;
   if (!attr) { int rc = set_smem_attr(kern, Tile<BN>::SMEM_BYTES); if (rc) return rc; attr = true; }
   int grid = g.tiles_m * g.tiles_n; if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, A_TMA ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(ta, tb, tout, g);
+  if (STATS) {                 // one column block per CTA: tile = blockIdx.x + i*gridDim.x keeps tn fixed
+    grid = grid / g.tiles_n * g.tiles_n;
+    if (grid < g.tiles_n) grid = g.tiles_n;
+  }
+  kern<<<grid, A_TMA ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(ta, tb, tout, g, bn_sums);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
 
-template <typename T, typename To, int BN, bool TMA_EPI>
-int dispatch_igemm2(bool a_tma, bool smallc, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
-                    const Geom& g, cudaStream_t st) {
-  if (a_tma) return launch_igemm<T, To, BN, true, false, TMA_EPI>(ta, tb, tout, g, st);
-  if (smallc) return launch_igemm<T, To, BN, false, true, TMA_EPI>(ta, tb, tout, g, st);
-  return launch_igemm<T, To, BN, false, false, TMA_EPI>(ta, tb, tout, g, st);
+template <typename T, typename To, int BN, bool TMA_EPI, bool STATS>
+int dispatch_igemm3(bool a_tma, bool smallc, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                    const Geom& g, double* bn_sums, cudaStream_t st) {
+  if (a_tma) return launch_igemm<T, To, BN, true, false, TMA_EPI, STATS>(ta, tb, tout, g, bn_sums, st);
+  if (smallc) return launch_igemm<T, To, BN, false, true, TMA_EPI, STATS>(ta, tb, tout, g, bn_sums, st);
+  return launch_igemm<T, To, BN, false, false, TMA_EPI, STATS>(ta, tb, tout, g, bn_sums, st);
+}
+template <typename T, typename To, int BN>
+int dispatch_igemm2(bool a_tma, bool smallc, bool tma_epi, const CUtensorMap& ta, const CUtensorMap& tb,
+                    const CUtensorMap& tout, const Geom& g, double* bn_sums, cudaStream_t st) {
+  if (tma_epi && bn_sums) return dispatch_igemm3<T, To, BN, true, true>(a_tma, smallc, ta, tb, tout, g, bn_sums, st);
+  if (tma_epi) return dispatch_igemm3<T, To, BN, true, false>(a_tma, smallc, ta, tb, tout, g, nullptr, st);
+  return dispatch_igemm3<T, To, BN, false, false>(a_tma, smallc, ta, tb, tout, g, nullptr, st);
 }
 template <typename T, typename To>
 int dispatch_igemm(int bn, bool a_tma, bool smallc, bool tma_epi, const CUtensorMap& ta, const CUtensorMap& tb,
-                   const CUtensorMap& tout, const Geom& g, cudaStream_t st) {
-  if (tma_epi) {
-    if (bn == 256) return dispatch_igemm2<T, To, 256, true>(a_tma, smallc, ta, tb, tout, g, st);
-    if (bn == 128) return dispatch_igemm2<T, To, 128, true>(a_tma, smallc, ta, tb, tout, g, st);
-    return dispatch_igemm2<T, To, 64, true>(a_tma, smallc, ta, tb, tout, g, st);
-  }
-  if (bn == 256) return dispatch_igemm2<T, To, 256, false>(a_tma, smallc, ta, tb, tout, g, st);
-  if (bn == 128) return dispatch_igemm2<T, To, 128, false>(a_tma, smallc, ta, tb, tout, g, st);
-  return dispatch_igemm2<T, To, 64, false>(a_tma, smallc, ta, tb, tout, g, st);
+                   const CUtensorMap& tout, const Geom& g, cudaStream_t st, double* bn_sums = nullptr) {
+  if (bn == 256) return dispatch_igemm2<T, To, 256>(a_tma, smallc, tma_epi, ta, tb, tout, g, bn_sums, st);
+  if (bn == 128) return dispatch_igemm2<T, To, 128>(a_tma, smallc, tma_epi, ta, tb, tout, g, bn_sums, st);
+  return dispatch_igemm2<T, To, 64>(a_tma, smallc, tma_epi, ta, tb, tout, g, bn_sums, st);
 }
 
 // Shared driver for fprop (mode 0) and dgrad (mode 1).
 //   gathered tensor [N][Hs][Ws][Cs]; GEMM rows = N*P*Q; weights wk [n_out][Kp]
 int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, int out_dtype, int64_t N, int64_t Hs,
               int64_t Ws, int64_t Cs, int64_t P, int64_t Q, int64_t n_out, int64_t R, int64_t S, int64_t stride,
-              cudaStream_t st, const char* what) {
+              cudaStream_t st, const char* what, double* bn_sums = nullptr) {
   const int es = dtype == SIMCLR_BF16 ? 2 : 4;
   const int KBE = 128 / es, CH = 16 / es;
   const bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);
@@ -722,9 +784,14 @@ int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, i
   const bool tma_epi = aligned16(out) && ((n_out * eo) % 16 == 0);
   if (tma_epi) { rc = make_tmap_2d(&tout, out, eo, (uint64_t)M, (uint64_t)n_out, (uint64_t)n_out * eo, 128, (uint32_t)(128 / eo)); if (rc) return rc; }
   else tout = tb;
-  if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_BF16) return dispatch_igemm<__nv_bfloat16, __nv_bfloat16>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st);
-  if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_F32) return dispatch_igemm<__nv_bfloat16, float>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st);
-  if (dtype == SIMCLR_F32 && out_dtype == SIMCLR_F32) return dispatch_igemm<float, float>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st);
+  if (bn_sums) {
+    if (!tma_epi) { set_error("%s: fused BN statistics need 16-byte aligned output rows", what); return SIMCLR_ERR_UNSUPPORTED; }
+    cudaError_t e = cudaMemsetAsync(bn_sums, 0, 2 * (size_t)n_out * sizeof(double), st);
+    if (e != cudaSuccess) { set_error("%s: memset: %s", what, cudaGetErrorString(e)); return (int)e; }
+  }
+  if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_BF16) return dispatch_igemm<__nv_bfloat16, __nv_bfloat16>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st, bn_sums);
+  if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_F32) return dispatch_igemm<__nv_bfloat16, float>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st, bn_sums);
+  if (dtype == SIMCLR_F32 && out_dtype == SIMCLR_F32) return dispatch_igemm<float, float>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st, bn_sums);
   set_error("%s: unsupported dtype combination %d -> %d", what, dtype, out_dtype);
   return SIMCLR_ERR_UNSUPPORTED;
 }
@@ -838,13 +905,14 @@ using namespace simclr;
 extern "C" {
 
 int simclr_conv2d_fprop_tc(const void* x, const void* wf, void* y, int dtype, int y_dtype, int64_t N, int64_t H,
-                           int64_t W, int64_t Cs, int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream) {
+                           int64_t W, int64_t Cs, int64_t Cout, int64_t R, int64_t S, int64_t stride, double* bn_sums,
+                           void* stream) {
   SIMCLR_CHECK_ARG(x && wf && y, "conv2d_fprop_tc: null pointer");
   SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cs > 0 && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
                    "conv2d_fprop_tc: bad geometry");
   const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   return tc::run_igemm(0, x, wf, y, dtype, y_dtype, N, H, W, Cs, Ho, Wo, Cout, R, S, stride, (cudaStream_t)stream,
-                       "conv2d_fprop_tc");
+                       "conv2d_fprop_tc", bn_sums);
 }
 
 int simclr_conv2d_dgrad_tc(const void* dy, const void* wd, void* dx, int dtype, int dx_dtype, int64_t N, int64_t H,

@@ -92,3 +92,62 @@ def preprocess_for_train_batch(images, draws, height, width, out=None, channel_o
     lib.augment(src, t(np.asarray(offs, dtype=np.int64)), t(np.asarray(hw, dtype=np.int32)), t(box), t(flip), t(col),
                 out, n, height, width, out.shape[3], channel_offset, stream_ptr())
     return out
+
+
+# ---------------------------------------------------------------------------
+# The reference's per-image entry point (tf2/data_util.py:497-518) and its random draws
+# ---------------------------------------------------------------------------
+
+def draw_train_augmentation(src_h, src_w, color_jitter_strength=1.0, rng=None):
+    """Host-side draws of `preprocess_for_train` (tf2/data_util.py:443-475) with the reference's
+    distributions: crop via the `sample_distorted_bounding_box` rule (aspect ~ U[3/4, 4/3], area in
+    [0.08, 1] of the image, accepted iff it covers >= 10 % (min_object_covered with the whole-image
+    box), <= 100 attempts, else the whole image -- SURVEY.md A9), flip ~ B(0.5), colour jitter
+    with p 0.8 (brightness / contrast / saturation factors and hue delta from `color_jitter`,
+    tf2/data_util.py:53-75, random op order), grayscale with p 0.2."""
+    import math
+    import random
+    rng = rng or random
+    box = (0, 0, src_h, src_w)
+    area = float(src_h * src_w)
+    for _ in range(100):
+        aspect = rng.uniform(3. / 4, 4. / 3)
+        min_h = int(round(math.sqrt(0.08 * area / aspect)))
+        max_h = int(round(math.sqrt(1.0 * area / aspect)))
+        if max_h * aspect > src_w:
+            max_h = int((src_w + 0.5 - 1e-7) / aspect)
+        max_h = min(max_h, src_h)
+        h = min(min_h, max_h)
+        if h < max_h:
+            h += rng.randint(0, max_h - h)
+        w = int(round(h * aspect))
+        if h <= 0 or w <= 0 or h > src_h or w > src_w:
+            continue
+        if w * h < 0.1 * area:          # min_object_covered = 0.1 of the whole-image bounding box
+            continue
+        y = rng.randint(0, src_h - h)
+        x = rng.randint(0, src_w - w)
+        box = (y, x, h, w)
+        break
+    s = color_jitter_strength
+    perm = [0, 1, 2, 3]
+    rng.shuffle(perm)
+    color = dict(apply_jitter=(s > 0 and rng.random() < 0.8), perm=tuple(perm),
+                 brightness=rng.uniform(max(1.0 - 0.8 * s, 0), 1.0 + 0.8 * s),
+                 contrast=rng.uniform(1 - 0.8 * s, 1 + 0.8 * s), saturation=rng.uniform(1 - 0.8 * s, 1 + 0.8 * s),
+                 hue=rng.uniform(-0.2 * s, 0.2 * s), apply_gray=(s > 0 and rng.random() < 0.2))
+    return dict(box=box, flip=rng.random() < 0.5, color=color)
+
+
+def preprocess_image(image, height, width, is_training=False, color_jitter_strength=0., test_crop=True, draws=None):
+    """Preprocesses the given image (tf2/data_util.py:497-518; same arguments).
+
+    image: uint8 tensor [Hs,Ws,3].  Training path only (`preprocess_for_train` on device);
+    the eval path (`center_crop`) is outside the pretrain step.  `draws` injects the random draws."""
+    if not is_training:
+        raise NotImplementedError('preprocess_for_eval (center crop) is not on the B200 pretrain path')
+    if draws is None:
+        draws = draw_train_augmentation(image.shape[0], image.shape[1], color_jitter_strength)
+    if color_jitter_strength <= 0:
+        draws = dict(draws, color=dict(draws['color'], apply_jitter=False, apply_gray=False))
+    return preprocess_for_train_batch([image], [draws], height, width)[0]

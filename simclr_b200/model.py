@@ -107,12 +107,14 @@ class LinearLayer:
         rows = inputs.shape[0]
         y_dtype = out_dtype if (out_dtype is not None and not self.use_bn) else (
             torch.float32 if out_dtype == torch.float32 else None)
-        y = self.op.forward(inputs.view(rows, 1, 1, self.cin), training, out_dtype=y_dtype).view(rows, self.num_classes)
+        sums = e.empty((2 * self.num_classes,), torch.float64) if (self.use_bn and training) else None
+        y = self.op.forward(inputs.view(rows, 1, 1, self.cin), training, out_dtype=y_dtype,
+                            bn_sums=sums).view(rows, self.num_classes)
         if self.bias is not None:
             assert y.dtype == torch.float32
             lib.bias_add(y, self.bias.value, rows, self.num_classes, stream_ptr())
         if self.use_bn:
-            y = self.bn_relu(y, training, relu=relu, out_dtype=out_dtype)
+            y = self.bn_relu(y, training, relu=relu, out_dtype=out_dtype, sums=sums)
         return y
 
     def backward(self, d, need_dx=True):
@@ -197,8 +199,8 @@ class Model:
         e = get_engine()
         self.vs = VarStore()
         self.resnet_model = resnet.resnet(
-            self.vs, resnet_depth=FLAGS.resnet_depth, width_multiplier=FLAGS.width_multiplier,
-            cifar_stem=FLAGS.image_size <= 32)
+            resnet_depth=FLAGS.resnet_depth, width_multiplier=FLAGS.width_multiplier,
+            cifar_stem=FLAGS.image_size <= 32, vs=self.vs)
         self._projection_head = ProjectionHead(self.vs, self.resnet_model.cout)
         if FLAGS.train_mode == 'finetune' or FLAGS.lineareval_while_pretraining:
             self.supervised_head = SupervisedHead(num_classes, self.vs, self.resnet_model.cout)

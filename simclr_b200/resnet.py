@@ -33,7 +33,8 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
         self.moving_variance = vs.add(pre + '/moving_variance:0', (channels,), 'ones', trainable=False)
         self.saved = None
 
-    def __call__(self, inputs, training, residual=None, relu=None, out_dtype=None):
+    def __call__(self, inputs, training, residual=None, relu=None, out_dtype=None, sums=None):
+        """`sums`: [2C] fp64 sum / sum of squares already produced by the conv epilogue."""
         e = get_engine()
         relu = self.relu if relu is None else relu
         C = self.C
@@ -45,8 +46,9 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
         g = None if self.gamma is None else self.gamma.value
         b = None if self.beta is None else self.beta.value
         if training:
-            sums = e.empty((2 * C,), torch.float64)
-            lib.bn_stats(y, e.code(y.dtype), rows, C, sums, st)
+            if sums is None:
+                sums = e.empty((2 * C,), torch.float64)
+                lib.bn_stats(y, e.code(y.dtype), rows, C, sums, st)
             count = float(rows)
             if e.sync_bn:            # SyncBatchNormalization: all-reduce sum x, sum x^2 (C2)
                 e.ctx.all_reduce_sum(sums)
@@ -130,7 +132,7 @@ class ConvOp:
         e.profile.append((kind, (N, H, W, self.cin, self.cout, self.R, s), flops, ev0, ev1))
         return r
 
-    def forward(self, x, training, out_dtype=None):
+    def forward(self, x, training, out_dtype=None, bn_sums=None):
         e = get_engine()
         N, H, W, Cs = x.shape
         assert Cs == self.cs, (x.shape, self.cs)
@@ -141,10 +143,12 @@ class ConvOp:
         if e.conv_engine == 'tc':
             self._pack(e)
             self._timed(e, 'fprop', x.shape, lambda: lib.conv2d_fprop_tc(
-                x, self.wf, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs, self.cout, self.R, self.S, s, st))
+                x, self.wf, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs, self.cout, self.R, self.S, s, bn_sums, st))
         else:
             lib.conv2d_fprop_simt(x, self.kernel.value, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs,
                                   self.cin, self.cout, self.R, self.S, s, st)
+            if bn_sums is not None:
+                lib.bn_stats(y, e.code(y.dtype), y.numel() // self.cout, self.cout, bn_sums, st)
         if training:
             self.saved_x = x
         return y
@@ -177,6 +181,18 @@ class ConvOp:
             lib.conv2d_dgrad_simt(dy, self.kernel.value, dx, e.code(dy.dtype), e.code(dx.dtype), N, H, W,
                                   self.cin, self.cout, self.R, self.S, self.stride, st)
         return dx
+
+
+def conv_bn(conv, bn, x, training, **bn_kwargs):
+    """conv -> BatchNorm with the batch statistics produced by the conv epilogue
+    (one pass over the conv output saved per layer)."""
+    e = get_engine()
+    op = conv.op if hasattr(conv, 'op') else conv
+    if not training:
+        return bn(op.forward(x, training), training, **bn_kwargs)
+    sums = e.empty((2 * op.cout,), torch.float64)
+    y = op.forward(x, training, bn_sums=sums)
+    return bn(y, training, sums=sums, **bn_kwargs)
 
 
 class Conv2dFixedPadding:  # pylint: disable=missing-docstring
@@ -220,7 +236,7 @@ class _Shortcut:
             lib.avgpool2x2_fwd(x, y, e.code(x.dtype), N, H, W, C, s, stream_ptr())
             self.in_shape = (N, H, W, C)
             x = y
-        return self.bn(self.conv(x, training), training)
+        return conv_bn(self.conv, self.bn, x, training)
 
     def backward(self, d):
         d = self.conv.backward(self.bn.backward(d))
@@ -259,7 +275,7 @@ class SK_Conv2D:  # pylint: disable=invalid-name
         e = get_engine()
         st = stream_ptr()
         f = self.filters
-        x = self.batch_norm_relu(self.conv2d_fixed_padding(inputs, training), training)     # [N,H,W,2f]
+        x = conv_bn(self.conv2d_fixed_padding, self.batch_norm_relu, inputs, training)      # [N,H,W,2f]
         N, H, W, _ = x.shape
         HW = H * W
         g32 = e.empty((N, f), torch.float32)
@@ -315,9 +331,8 @@ class ResidualBlock:  # pylint: disable=missing-docstring
 
     def __call__(self, inputs, training):
         shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
-        x = self.b1(self.c1(inputs, training), training)
-        x = self.c2(x, training)
-        return self.b2(x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :382
+        x = conv_bn(self.c1, self.b1, inputs, training)
+        return conv_bn(self.c2, self.b2, x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :382
 
     def backward(self, d_out, d_out2=None):
         dy = self.b2.backward(d_out, d_out2)      # d_out <- (d_out + d_out2) * [out > 0]
@@ -348,10 +363,9 @@ class BottleneckBlock:
 
     def __call__(self, inputs, training):
         shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
-        x = self.b1(self.c1(inputs, training), training)
-        x = self.sk(x, training) if self.sk is not None else self.b2(self.c2(x, training), training)
-        x = self.c3(x, training)
-        return self.b3(x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :487
+        x = conv_bn(self.c1, self.b1, inputs, training)
+        x = self.sk(x, training) if self.sk is not None else conv_bn(self.c2, self.b2, x, training)
+        return conv_bn(self.c3, self.b3, x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :487
 
     def backward(self, d_out, d_out2=None):
         dy = self.b3.backward(d_out, d_out2)
@@ -428,12 +442,14 @@ class Resnet:  # pylint: disable=missing-docstring
     def __call__(self, inputs, training, endpoints=None):
         e = get_engine()
         st = stream_ptr()
-        x = self.stem_conv(inputs, training)
         if endpoints is not None:
+            x = self.stem_conv(inputs, training)
             endpoints['initial_conv'] = x
-        x = self.stem_bn(x, training)
+            x = self.stem_bn(x, training)
+        else:
+            x = conv_bn(self.stem_conv, self.stem_bn, inputs, training)
         for conv, bn in self.stem_extra:
-            x = bn(conv(x, training), training)
+            x = conv_bn(conv, bn, x, training)
         pool_saved = None
         if not self.cifar_stem:                                   # MaxPooling2D(3, 2, 'SAME'), :605-611
             N, H, W, C = x.shape
@@ -488,13 +504,22 @@ MODEL_PARAMS = {  # tf2/resnet.py:709-734
 }
 
 
-def resnet(vs, resnet_depth, width_multiplier, cifar_stem=False, data_format='channels_last',
-           dropblock_keep_probs=None, dropblock_size=None):
-    """tf2/resnet.py:702-747.  Only `channels_last` exists on this path."""
+def resnet(resnet_depth, width_multiplier, cifar_stem=False, data_format='channels_last',
+           dropblock_keep_probs=None, dropblock_size=None, vs=None):
+    """Returns the ResNet model for a given size (tf2/resnet.py:702-747, same arguments).
+
+    `vs` (this implementation only): the `engine.VarStore` the variables are registered in; a
+    fresh one is created when omitted (exposed as `.vs`, call `.vs.materialize(device)` before
+    use).  Only `channels_last` exists on this path."""
+    from .engine import VarStore
     if resnet_depth not in MODEL_PARAMS:
         raise ValueError('Not a valid resnet_depth:', resnet_depth)
     if data_format != 'channels_last':
         raise ValueError('only channels_last is supported')
     del dropblock_keep_probs, dropblock_size      # DropBlock is never enabled by the reference
     block_fn, layers = MODEL_PARAMS[resnet_depth]
-    return Resnet(vs, block_fn, layers, width_multiplier, cifar_stem=cifar_stem)
+    if vs is None:
+        vs = VarStore()
+    net = Resnet(vs, block_fn, layers, width_multiplier, cifar_stem=cifar_stem)
+    net.vs = vs
+    return net

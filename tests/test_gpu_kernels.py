@@ -415,3 +415,17 @@ def test_sk_conv2d_fwd_bwd(eng, flags, strides):
     assert rel_err(dx, xo.grad) < 1e-4
     for v in vs.trainable:
         assert rel_err(v.grad, P[v.name].grad) < 2e-4, v.name
+
+
+def test_preprocess_image_entry_point(eng):
+    """`preprocess_image(image, h, w, is_training, color_jitter_strength, test_crop)` (tf2/data_util.py:497-518)."""
+    from oracle import data_util as OD
+    from simclr_b200 import data_util as D
+    g = torch.Generator().manual_seed(9)
+    im = torch.randint(0, 256, (120, 160, 3), dtype=torch.uint8, generator=g)
+    d = D.draw_train_augmentation(120, 160, 1.0)
+    out = D.preprocess_image(im, 64, 64, is_training=True, color_jitter_strength=1.0, draws=d)
+    ref = OD.preprocess_for_train(im.double() / 255.0, 64, 64, d)
+    assert out.shape == (64, 64, 3) and (out.cpu().double() - ref).abs().max() < 2e-5
+    with pytest.raises(NotImplementedError):
+        D.preprocess_image(im, 64, 64, is_training=False)

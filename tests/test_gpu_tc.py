@@ -62,8 +62,14 @@ def test_tc_fprop_bf16(case, out_dtype):
     yo = conv_reference(x.double(), w.double(), k, s)
     wf, _ = _pack(w, torch.bfloat16, k, Cin, Cs, Cout, want_wd=False)
     y = torch.full(yo.shape, float('nan'), dtype=out_dtype, device='cuda')
-    lib.conv2d_fprop_tc(xs.cuda(), wf, y, 1, DTYPE_CODE[out_dtype], N, H, W, Cs, Cout, k, k, s, stream_ptr())
+    sums = torch.full((2 * Cout,), float('nan'), dtype=torch.float64, device='cuda') if (Cout * y.element_size()) % 16 == 0 else None
+    lib.conv2d_fprop_tc(xs.cuda(), wf, y, 1, DTYPE_CODE[out_dtype], N, H, W, Cs, Cout, k, k, s, sums, stream_ptr())
     torch.cuda.synchronize()
+    # BatchNorm statistics fused into the epilogue: sums of the *stored* outputs
+    yf = y.double().reshape(-1, Cout)
+    if sums is not None:
+        assert rel_err(sums[:Cout], yf.sum(0)) < 1e-5
+        assert rel_err(sums[Cout:], (yf * yf).sum(0)) < 1e-5
     assert rel_err(y, yo) < (2e-4 if out_dtype == torch.float32 else 8e-3)
 
 
@@ -111,7 +117,7 @@ def test_tc_tf32(case):
     wf, wd = _pack(w, torch.float32, k, Cin, Cs, Cout)
     st = stream_ptr()
     y = torch.full(yo.shape, float('nan'), device='cuda')
-    lib.conv2d_fprop_tc(xs.cuda(), wf, y, 0, 0, N, H, W, Cs, Cout, k, k, s, st)
+    lib.conv2d_fprop_tc(xs.cuda(), wf, y, 0, 0, N, H, W, Cs, Cout, k, k, s, None, st)
     dx = torch.full((N, H, W, Cin), float('nan'), device='cuda')
     lib.conv2d_dgrad_tc(dy.cuda(), wd, dx, 0, 0, N, H, W, Cin, Cout, k, k, s, st)
     torch.cuda.synchronize()
@@ -137,7 +143,7 @@ def test_tc_matches_simt_large():
     st = stream_ptr()
     wf32 = w.float().contiguous()
     y_tc = torch.empty(N, H, W, C, device='cuda'); y_ref = torch.empty_like(y_tc)
-    lib.conv2d_fprop_tc(x, wf, y_tc, 1, 0, N, H, W, C, C, k, k, s, st)
+    lib.conv2d_fprop_tc(x, wf, y_tc, 1, 0, N, H, W, C, C, k, k, s, None, st)
     lib.conv2d_fprop_simt(x, wf32, y_ref, 1, 0, N, H, W, C, C, C, k, k, s, st)
     dx_tc = torch.empty(N, H, W, C, device='cuda'); dx_ref = torch.empty_like(dx_tc)
     lib.conv2d_dgrad_tc(dy, wd, dx_tc, 1, 0, N, H, W, C, C, k, k, s, st)

@@ -29,7 +29,7 @@ def test_argument_errors_are_reported_without_a_gpu():
         lib.ntxent_normalize(None, 4, 8, 1, None, None, None)
     assert 'null pointer' in str(ei.value)
     with pytest.raises(SimclrError):
-        lib.conv2d_fprop_tc(1, 1, 1, 1, 1, 1, 8, 8, 8, 8, 2, 2, 1, None)     # even kernel size
+        lib.conv2d_fprop_tc(1, 1, 1, 1, 1, 1, 8, 8, 8, 8, 2, 2, 1, None, None)     # even kernel size
 
 
 def test_flag_surface(flags):
@@ -70,7 +70,7 @@ def test_variable_inventory_matches_oracle(flags, kw):
     from util import cfg_from_flags
     flags.set_flags(**kw)
     vs = engine.VarStore()
-    net = resnet.resnet(vs, flags.FLAGS.resnet_depth, flags.FLAGS.width_multiplier, cifar_stem=flags.FLAGS.image_size <= 32)
+    net = resnet.resnet(flags.FLAGS.resnet_depth, flags.FLAGS.width_multiplier, cifar_stem=flags.FLAGS.image_size <= 32, vs=vs)
     model.ProjectionHead(vs, net.cout)
     model.SupervisedHead(1000, vs, net.cout)
     om = OM.Model(cfg_from_flags(flags.FLAGS), 1000)
@@ -105,7 +105,7 @@ def test_lars_name_filters(flags):
 def test_model_errors(flags):
     from simclr_b200 import resnet, engine
     with pytest.raises(ValueError):
-        resnet.resnet(engine.VarStore(), 51, 1)
+        resnet.resnet(51, 1)
 
 
 # ---- multi-replica plumbing over gloo (2 ranks on CPU) ------------------------
@@ -155,3 +155,23 @@ def test_replica_context_gloo_world2():
         assert p.exitcode == 0
     got = sorted(q.get(timeout=5) for _ in range(2))
     assert got == [(0, 'ok'), (1, 'ok')]
+
+
+def test_augmentation_draws_follow_the_reference_ranges():
+    """`draw_train_augmentation` reproduces the distributions of tf2/data_util.py:53-75,246-320,382-390."""
+    import random
+    from simclr_b200 import data_util
+    rng = random.Random(1)
+    n_flip = n_jit = n_gray = 0
+    for _ in range(400):
+        d = data_util.draw_train_augmentation(240, 320, 1.0, rng)
+        y, x, h, w = d['box']
+        assert 0 <= y and 0 <= x and y + h <= 240 and x + w <= 320
+        assert h * w >= 0.1 * 240 * 320 - 1e-9                      # min_object_covered (A9)
+        assert 0.70 <= w / h <= 1.40                                  # aspect in [3/4, 4/3] up to rounding
+        c = d['color']
+        assert sorted(c['perm']) == [0, 1, 2, 3]
+        assert 0.2 <= c['brightness'] <= 1.8 and 0.2 <= c['contrast'] <= 1.8 and 0.2 <= c['saturation'] <= 1.8
+        assert -0.2 <= c['hue'] <= 0.2
+        n_flip += d['flip']; n_jit += c['apply_jitter']; n_gray += c['apply_gray']
+    assert 150 < n_flip < 250 and 280 < n_jit < 360 and 40 < n_gray < 120
