@@ -60,41 +60,49 @@ bn_reduce_kernel(T* __restrict__ a, const T* __restrict__ a2, const T* __restric
       for (int i = 0; i < 8; ++i) { mu[i] = mean[cv * 8 + i]; rs[i] = rstd[cv * 8 + i]; }
     }
     if (active) {
-      for (int64_t r = r0 + ty; r < r1; r += row_lanes) {
-        const int64_t off = r * C + (int64_t)cv * 8;
-        float v[8];
-        load8<T>(a + off, v);
-        if (MODE == 0) {
+      if (MODE == 0) {
+        for (int64_t r = r0 + ty; r < r1; r += row_lanes) {
+          float v[8];
+          load8<T>(a + r * C + (int64_t)cv * 8, v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) { s0[i] += v[i]; s1[i] = fmaf(v[i], v[i], s1[i]); }
-        } else {
-          bool dirty = false;
-          if (a2 != nullptr) {
-            float w[8]; load8<T>(a2 + off, w);
+        }
+      } else {
+        // two rows per iteration: all loads of both rows are issued before any arithmetic
+        for (int64_t r = r0 + ty; r < r1; r += 2 * row_lanes) {
+          const int64_t off0 = r * C + (int64_t)cv * 8;
+          const bool has1 = r + row_lanes < r1;
+          const int64_t off1 = has1 ? (r + row_lanes) * C + (int64_t)cv * 8 : off0;
+          float v[2][8], w[2][8], z[2][8], yy[2][8];
+          load8<T>(a + off0, v[0]); load8<T>(a + off1, v[1]);
+          if (a2 != nullptr) { load8<T>(a2 + off0, w[0]); load8<T>(a2 + off1, w[1]); }
+          if (zmask != nullptr) { load8<T>(zmask + off0, z[0]); load8<T>(zmask + off1, z[1]); }
+          load8<Ty>(y + off0, yy[0]); load8<Ty>(y + off1, yy[1]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += w[i];
-            dirty = true;
-          }
-          if (zmask != nullptr) {
-            float z[8]; load8<T>(zmask + off, z);
+          for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !has1) break;
+            if (a2 != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (z[i] > 0.f) ? v[i] : 0.f;
-            dirty = true;
-          }
-          if (dirty) {
-            store8<T>(a + off, v);
-            // keep the sums consistent with what phase 2 will read back
-            if (sizeof(T) == 2) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = to_f<T>(from_f<T>(v[i]));
+              for (int i = 0; i < 8; ++i) v[u][i] += w[u][i];
             }
-          }
-          float yy[8]; load8<Ty>(y + off, yy);
+            if (zmask != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float xh = (yy[i] - mu[i]) * rs[i];
-            s0[i] += v[i];
-            s1[i] = fmaf(v[i], xh, s1[i]);
+              for (int i = 0; i < 8; ++i) v[u][i] = (z[u][i] > 0.f) ? v[u][i] : 0.f;
+            }
+            if (a2 != nullptr || zmask != nullptr) {
+              store8<T>(a + (u == 0 ? off0 : off1), v[u]);
+              // keep the sums consistent with what phase 2 will read back
+              if (sizeof(T) == 2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[u][i] = to_f<T>(from_f<T>(v[u][i]));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float xh = (yy[u][i] - mu[i]) * rs[i];
+              s0[i] += v[u][i];
+              s1[i] = fmaf(v[u][i], xh, s1[i]);
+            }
           }
         }
       }
