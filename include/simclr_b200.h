@@ -229,6 +229,17 @@ SIMCLR_API int simclr_sk_mix_bwd_reduce(const void* dout, const void* x, const f
 /* dx[n,hw,s*f+c] = dout[n,hw,c]*m_s[n,c] + dg[n,c]/HW  (dg: gradient w.r.t. the pooled features) */
 SIMCLR_API int simclr_sk_mix_bwd_apply(const void* dout, const float* mixing, const float* dg, void* dx, int dtype,
                                        int64_t N, int64_t HW, int64_t f, void* stream);
+/* Squeeze-and-excitation (tf2/resnet.py:280-311): out = sigmoid(l[n,c]) * x[n,hw,c]; backward
+ * dl = sigma'(l) * sum_hw dout*x and dx = dout*sigmoid(l) + dmean[n,c]/HW.  The two tiny
+ * "1x1 convs" of the gate run on the dense path (simclr_conv2d_*_simt with H=W=1, any width). */
+SIMCLR_API int simclr_se_scale_fwd(const void* x, const float* logits, void* out, int dtype, int64_t N,
+                                   int64_t HW, int64_t C, void* stream);
+SIMCLR_API int simclr_se_scale_bwd_reduce(const void* dout, const void* x, const float* logits, float* dlogits,
+                                          int dtype, int64_t N, int64_t HW, int64_t C, void* stream);
+SIMCLR_API int simclr_se_scale_bwd_apply(const void* dout, const float* logits, const float* dmean, void* dx,
+                                         int dtype, int64_t N, int64_t HW, int64_t C, void* stream);
+/* mask_src == NULL: x = max(x, 0); else x = x * [mask_src > 0]   (fp32, in place) */
+SIMCLR_API int simclr_relu_inplace(float* x, const float* mask_src, int64_t n, void* stream);
 /* AveragePooling2D(2, stride): stride 2 = FixedPadding(2) + 'VALID'; stride 1 = 'SAME' with the
  * divisor counting valid elements only.  x [N,H,W,C]. */
 SIMCLR_API int simclr_avgpool2x2_fwd(const void* x, void* y, int dtype, int64_t N, int64_t H, int64_t W, int64_t C,

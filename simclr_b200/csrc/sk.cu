@@ -120,6 +120,57 @@ __global__ void avgpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out,
   }
 }
 
+// ---- squeeze-and-excitation (tf2/resnet.py:280-311) ------------------------------------------
+// out = sigmoid(l[n,c]) * x[n,hw,c]
+template <typename T>
+__global__ void se_scale_fwd_kernel(const T* __restrict__ x, const float* __restrict__ logits, T* __restrict__ out,
+                                    int64_t total, int HW, int C) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t n = idx / ((int64_t)HW * C);
+    const float g = 1.f / (1.f + expf(-logits[n * C + c]));
+    out[idx] = from_f<T>(to_f<T>(x[idx]) * g);
+  }
+}
+// dl[n,c] = sigma'(l) * sum_hw dout*x
+template <typename T>
+__global__ void se_scale_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ x,
+                                           const float* __restrict__ logits, float* __restrict__ dlogits, int64_t N,
+                                           int HW, int C) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * C) return;
+  const int64_t n = idx / C; const int c = (int)(idx % C);
+  float d = 0.f;
+  for (int i = 0; i < HW; ++i) {
+    const int64_t o = (n * HW + i) * (int64_t)C + c;
+    d = fmaf(to_f<T>(dout[o]), to_f<T>(x[o]), d);
+  }
+  const float g = 1.f / (1.f + expf(-logits[idx]));
+  dlogits[idx] = d * g * (1.f - g);
+}
+// dx = dout*sigmoid(l) + dmean[n,c]/HW   (dmean: gradient w.r.t. the squeezed mean)
+template <typename T>
+__global__ void se_scale_bwd_apply_kernel(const T* __restrict__ dout, const float* __restrict__ logits,
+                                          const float* __restrict__ dmean, T* __restrict__ dx, int64_t total, int HW,
+                                          int C) {
+  const float inv = 1.f / (float)HW;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t n = idx / ((int64_t)HW * C);
+    const float g = 1.f / (1.f + expf(-logits[n * C + c]));
+    dx[idx] = from_f<T>(fmaf(to_f<T>(dout[idx]), g, dmean[n * C + c] * inv));
+  }
+}
+// y = max(x, 0) in place / dx = dy * [y > 0] in place, fp32 [n]
+__global__ void relu_kernel(float* __restrict__ x, const float* __restrict__ mask_src, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (mask_src == nullptr) x[i] = fmaxf(x[i], 0.f);
+    else x[i] = mask_src[i] > 0.f ? x[i] : 0.f;
+  }
+}
+
 inline unsigned grid_for(int64_t total) {
   int64_t b = (total + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -179,6 +230,49 @@ int simclr_sk_mix_bwd_apply(const void* dout, const float* mixing, const float* 
   if (dtype == SIMCLR_F32) sk_mix_bwd_apply_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)dout, mixing, dg, (float*)dx, total, (int)HW, (int)f);
   else if (dtype == SIMCLR_BF16) sk_mix_bwd_apply_kernel<bf16><<<grid_for(total), 256, 0, st>>>((const bf16*)dout, mixing, dg, (bf16*)dx, total, (int)HW, (int)f);
   else { set_error("sk_mix_bwd_apply: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_se_scale_fwd(const void* x, const float* logits, void* out, int dtype, int64_t N, int64_t HW, int64_t C,
+                        void* stream) {
+  SIMCLR_CHECK_ARG(x && logits && out && N > 0 && HW > 0 && C > 0, "se_scale_fwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = N * HW * C;
+  if (dtype == SIMCLR_F32) se_scale_fwd_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)x, logits, (float*)out, total, (int)HW, (int)C);
+  else if (dtype == SIMCLR_BF16) se_scale_fwd_kernel<bf16><<<grid_for(total), 256, 0, st>>>((const bf16*)x, logits, (bf16*)out, total, (int)HW, (int)C);
+  else { set_error("se_scale_fwd: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_se_scale_bwd_reduce(const void* dout, const void* x, const float* logits, float* dlogits, int dtype,
+                               int64_t N, int64_t HW, int64_t C, void* stream) {
+  SIMCLR_CHECK_ARG(dout && x && logits && dlogits && N > 0 && HW > 0 && C > 0, "se_scale_bwd_reduce: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((N * C + 255) / 256);
+  if (dtype == SIMCLR_F32) se_scale_bwd_reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)dout, (const float*)x, logits, dlogits, N, (int)HW, (int)C);
+  else if (dtype == SIMCLR_BF16) se_scale_bwd_reduce_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dout, (const bf16*)x, logits, dlogits, N, (int)HW, (int)C);
+  else { set_error("se_scale_bwd_reduce: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_se_scale_bwd_apply(const void* dout, const float* logits, const float* dmean, void* dx, int dtype,
+                              int64_t N, int64_t HW, int64_t C, void* stream) {
+  SIMCLR_CHECK_ARG(dout && logits && dmean && dx && N > 0 && HW > 0 && C > 0, "se_scale_bwd_apply: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = N * HW * C;
+  if (dtype == SIMCLR_F32) se_scale_bwd_apply_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)dout, logits, dmean, (float*)dx, total, (int)HW, (int)C);
+  else if (dtype == SIMCLR_BF16) se_scale_bwd_apply_kernel<bf16><<<grid_for(total), 256, 0, st>>>((const bf16*)dout, logits, dmean, (bf16*)dx, total, (int)HW, (int)C);
+  else { set_error("se_scale_bwd_apply: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_relu_inplace(float* x, const float* mask_src, int64_t n, void* stream) {
+  SIMCLR_CHECK_ARG(x && n > 0, "relu_inplace: bad args");
+  relu_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, mask_src, n);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }

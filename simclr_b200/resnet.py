@@ -7,8 +7,8 @@ Class names, constructor arguments and the `resnet()` factory mirror
 `backward(grad)`.  Activations are NHWC torch tensors in the engine's activation
 dtype; variables are fp32 HWIO / [C] views into flat buffers.
 
-SK blocks (`sk_ratio > 0`, with the ResNet-D stem and shortcuts, config 5) are
-on the GPU path; SE (`se_ratio > 0`, in no BASELINE config) raises at construction.
+SK blocks (`sk_ratio > 0`, with the ResNet-D stem and shortcuts, config 5) and SE
+blocks (`se_ratio > 0`) are on the GPU path.
 """
 import torch
 
@@ -317,6 +317,94 @@ class SK_Conv2D:  # pylint: disable=invalid-name
         return self.conv2d_fixed_padding.backward(d)
 
 
+class SE_Layer:  # pylint: disable=invalid-name
+    """Squeeze and Excitation layer (tf2/resnet.py:280-311).  The expand width follows the input
+    (SURVEY Q9).  The two gate "convs" act on [N,1,1,C] and are arbitrarily narrow (max(1,
+    int(filters*se_ratio))), so they run on the CUDA-core dense path in fp32."""
+
+    def __init__(self, vs, scope, cin, filters, se_ratio):
+        scope = scope + '/' + vs.namer('se_layer')
+        self.cin = cin
+        self.mid = max(1, int(filters * se_ratio))
+        c0 = vs.namer('conv2d')
+        self.reduce_kernel = vs.add('%s/%s/kernel:0' % (scope, c0), (1, 1, cin, self.mid), 'variance_scaling')
+        self.reduce_bias = vs.add('%s/%s/bias:0' % (scope, c0), (self.mid,), 'zeros')
+        c1 = vs.namer('conv2d')
+        self.expand_kernel = vs.add('%s/%s/kernel:0' % (scope, c1), (1, 1, self.mid, cin), 'variance_scaling')
+        self.expand_bias = vs.add('%s/%s/bias:0' % (scope, c1), (cin,), 'zeros')
+        self.saved = None
+
+    def __call__(self, inputs, training):
+        e = get_engine()
+        st = stream_ptr()
+        N, H, W, C = inputs.shape
+        m = e.empty((N, C), torch.float32)
+        lib.global_avgpool_fwd(inputs, e.code(inputs.dtype), m, F32, N, H * W, C, st)
+        h = e.empty((N, self.mid), torch.float32)
+        lib.conv2d_fprop_simt(m, self.reduce_kernel.value, h, F32, F32, N, 1, 1, C, C, self.mid, 1, 1, 1, st)
+        lib.bias_add(h, self.reduce_bias.value, N, self.mid, st)
+        lib.relu_inplace(h, None, h.numel(), st)
+        l = e.empty((N, C), torch.float32)
+        lib.conv2d_fprop_simt(h, self.expand_kernel.value, l, F32, F32, N, 1, 1, self.mid, self.mid, C, 1, 1, 1, st)
+        lib.bias_add(l, self.expand_bias.value, N, C, st)
+        out = e.empty(inputs.shape, inputs.dtype)
+        lib.se_scale_fwd(inputs, l, out, e.code(inputs.dtype), N, H * W, C, st)
+        if training:
+            self.saved = (inputs, m, h, l)
+        return out
+
+    def backward(self, dout):
+        e = get_engine()
+        st = stream_ptr()
+        x, m, h, l = self.saved
+        self.saved = None
+        N, H, W, C = x.shape
+        dl = e.empty((N, C), torch.float32)
+        lib.se_scale_bwd_reduce(dout, x, l, dl, e.code(dout.dtype), N, H * W, C, st)
+        lib.bias_grad(dl, self.expand_bias.grad, N, C, st)
+        lib.conv2d_wgrad_simt(h, dl, self.expand_kernel.grad, F32, N, 1, 1, self.mid, self.mid, C, 1, 1, 1, st)
+        dh = e.empty((N, self.mid), torch.float32)
+        lib.conv2d_dgrad_simt(dl, self.expand_kernel.value, dh, F32, F32, N, 1, 1, self.mid, C, 1, 1, 1, st)
+        lib.relu_inplace(dh, h, dh.numel(), st)
+        lib.bias_grad(dh, self.reduce_bias.grad, N, self.mid, st)
+        lib.conv2d_wgrad_simt(m, dh, self.reduce_kernel.grad, F32, N, 1, 1, C, C, self.mid, 1, 1, 1, st)
+        dm = e.empty((N, C), torch.float32)
+        lib.conv2d_dgrad_simt(dh, self.reduce_kernel.value, dm, F32, F32, N, 1, 1, C, self.mid, 1, 1, 1, st)
+        dx = e.empty(x.shape, x.dtype)
+        lib.se_scale_bwd_apply(dout, l, dm, dx, e.code(dout.dtype), N, H * W, C, st)
+        return dx
+
+
+class _AddRelu:
+    """relu(inputs + shortcut) as its own op (needed when an SE layer sits between the last BN
+    and the residual add, tf2/resnet.py:379-382,473-487)."""
+
+    def __init__(self):
+        self.saved = None
+
+    def __call__(self, x, shortcut, training):
+        e = get_engine()
+        C = x.shape[-1]
+        ones = torch.ones(C, dtype=torch.float32, device=e.device)
+        zeros = torch.zeros(C, dtype=torch.float32, device=e.device)
+        out = e.empty(x.shape, x.dtype)
+        lib.bn_apply(x, e.code(x.dtype), shortcut, out, e.code(out.dtype), x.numel() // C, C, ones, zeros, 1, stream_ptr())
+        if training:
+            self.saved = (out, ones, zeros)
+        return out
+
+    def backward(self, d_out, d_out2=None):
+        """d_out <- (d_out + d_out2) * [out > 0] in place; it is the gradient of both addends."""
+        e = get_engine()
+        out, ones, zeros = self.saved
+        self.saved = None
+        C = out.shape[-1]
+        scratch = e.empty((2 * C,), torch.float64)
+        lib.bn_bwd_reduce(d_out, d_out2, out, e.code(d_out.dtype), out, e.code(out.dtype), out.numel() // C, C,
+                          zeros, ones, scratch, stream_ptr())
+        return d_out
+
+
 class ResidualBlock:  # pylint: disable=missing-docstring
     """tf2/resnet.py:314-382."""
 
@@ -327,15 +415,24 @@ class ResidualBlock:  # pylint: disable=missing-docstring
         self.b1 = BatchNormRelu(vs, scope, filters)
         self.c2 = Conv2dFixedPadding(vs, scope, filters, filters, 3, 1)
         self.b2 = BatchNormRelu(vs, scope, filters, relu=False, init_zero=True)
+        self.se_layer = SE_Layer(vs, scope, filters, filters, FLAGS.se_ratio) if FLAGS.se_ratio > 0 else None
+        self.add_relu = _AddRelu() if self.se_layer is not None else None
         self.cout = filters
 
     def __call__(self, inputs, training):
         shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
         x = conv_bn(self.c1, self.b1, inputs, training)
+        if self.se_layer is not None:
+            x = self.se_layer(conv_bn(self.c2, self.b2, x, training), training)
+            return self.add_relu(x, shortcut, training)
         return conv_bn(self.c2, self.b2, x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :382
 
     def backward(self, d_out, d_out2=None):
-        dy = self.b2.backward(d_out, d_out2)      # d_out <- (d_out + d_out2) * [out > 0]
+        if self.se_layer is not None:
+            d_out = self.add_relu.backward(d_out, d_out2)
+            dy = self.b2.backward(self.se_layer.backward(d_out))
+        else:
+            dy = self.b2.backward(d_out, d_out2)      # d_out <- (d_out + d_out2) * [out > 0]
         d = self.c2.backward(dy)
         d = self.b1.backward(d)
         dx_a = self.c1.backward(d)
@@ -359,16 +456,26 @@ class BottleneckBlock:
             self.b2 = BatchNormRelu(vs, scope, filters)
         self.c3 = Conv2dFixedPadding(vs, scope, filters, 4 * filters, 1, 1)
         self.b3 = BatchNormRelu(vs, scope, 4 * filters, relu=False, init_zero=True)
+        # tf2/resnet.py:474-476 builds SE with `filters`; its expand width follows the input (4*filters)
+        self.se_layer = SE_Layer(vs, scope, 4 * filters, filters, FLAGS.se_ratio) if FLAGS.se_ratio > 0 else None
+        self.add_relu = _AddRelu() if self.se_layer is not None else None
         self.cout = 4 * filters
 
     def __call__(self, inputs, training):
         shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
         x = conv_bn(self.c1, self.b1, inputs, training)
         x = self.sk(x, training) if self.sk is not None else conv_bn(self.c2, self.b2, x, training)
+        if self.se_layer is not None:
+            x = self.se_layer(conv_bn(self.c3, self.b3, x, training), training)
+            return self.add_relu(x, shortcut, training)
         return conv_bn(self.c3, self.b3, x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :487
 
     def backward(self, d_out, d_out2=None):
-        dy = self.b3.backward(d_out, d_out2)
+        if self.se_layer is not None:
+            d_out = self.add_relu.backward(d_out, d_out2)
+            dy = self.b3.backward(self.se_layer.backward(d_out))
+        else:
+            dy = self.b3.backward(d_out, d_out2)
         d = self.c3.backward(dy)
         if self.sk is not None:
             d = self.sk.backward(d)
@@ -410,8 +517,6 @@ class Resnet:  # pylint: disable=missing-docstring
     STEM_CS = 4
 
     def __init__(self, vs, block_fn, layers, width_multiplier, cifar_stem=False):
-        if FLAGS.se_ratio > 0:
-            raise NotImplementedError('SE blocks are not on the B200 path yet (se_ratio must be 0)')
         scope = 'resnet'
         wm = width_multiplier
         self.cifar_stem = cifar_stem

@@ -429,3 +429,33 @@ def test_preprocess_image_entry_point(eng):
     assert out.shape == (64, 64, 3) and (out.cpu().double() - ref).abs().max() < 2e-5
     with pytest.raises(NotImplementedError):
         D.preprocess_image(im, 64, 64, is_training=False)
+
+
+def test_se_layer_fwd_bwd(eng, flags):
+    """SE_Layer (tf2/resnet.py:280-311) vs the oracle, including the gate MLP gradients."""
+    from oracle import resnet as OR
+    from simclr_b200 import resnet as R
+    from simclr_b200.engine import VarStore
+    torch.manual_seed(21)
+    N, H, W, C, filters, ratio = 5, 6, 6, 32, 32, 0.0625
+    vs = VarStore()
+    se = R.SE_Layer(vs, 's', C, filters, ratio)
+    vs.materialize(eng.device, seed=4)
+    for v in vs.trainable:
+        if 'bias' in v.name:
+            v.value.copy_(torch.randn(v.shape) * 0.3)
+    ovs = OR.VarStore()
+    ose = OR.SE_Layer(ovs, 's', C, filters, ratio)
+    assert [v.name for v in vs.trainable] == list(ovs.trainable)
+    P = {v.name: v.value.detach().cpu().double().requires_grad_(True) for v in vs.trainable}
+    x = torch.randn(N, H, W, C)
+    xo = x.double().requires_grad_(True)
+    yo = ose(P, {}, xo.permute(0, 3, 1, 2), True).permute(0, 2, 3, 1)
+    dy = torch.randn(yo.shape)
+    yo.backward(dy.double())
+    y = se(_dev(x), True)
+    assert rel_err(y, yo) < 1e-5
+    dx = se.backward(_dev(dy))
+    assert rel_err(dx, xo.grad) < 1e-5
+    for v in vs.trainable:
+        assert rel_err(v.grad, P[v.name].grad) < 1e-4, v.name

@@ -213,3 +213,33 @@ def test_loss_curve_matches_oracle(flags):
     print('loss curve ours', ours, 'oracle', ref)
     for a, b in zip(ours, ref):
         assert abs(a - b) < 1e-3 * abs(b), (ours, ref)
+
+
+def test_step_parity_se(flags):
+    """SE blocks (se_ratio > 0) end to end: ResNet-18 + SE, fp32 verification mode."""
+    from oracle import step as OS
+    from simclr_b200 import flags_def
+    B, S = 16, 64
+    flags_def.set_flags(se_ratio=0.0625)
+    trainer, om, P, S_ = _setup(flags, 'fp32', 'simt', False, B, S, depth=18, use_blur=False)
+    g = torch.Generator().manual_seed(3)
+    for k in P:                                   # non-zero SE biases so the gate is not at sigmoid(0)
+        if 'se_layer' in k and 'bias' in k:
+            P[k] = torch.randn(P[k].shape, generator=g) * 0.2
+    trainer.model.vs.load(P)
+    f, lab, _, _ = _data(B, S)
+    P64 = collections.OrderedDict((k, v.double()) for k, v in P.items())
+    S64 = collections.OrderedDict((k, v.double()) for k, v in S_.items())
+    i64 = OS.forward_backward(om, P64, S64, [f.double()], [lab.double()])
+    i32 = OS.forward_backward(om, P, S_, [f], [lab])
+    trainer.optimizer.learning_rate = 0.0
+    loss = trainer.single_step(f.cuda(), lab.cuda())
+    torch.cuda.synchronize()
+    assert abs(loss.item() - i64['loss'].item()) < 1e-4 * abs(i64['loss'].item())
+    for v in trainer.model.trainable_variables:
+        ref = i64['grads'][v.name]
+        err = rel_err(v.grad, ref)
+        if ref.norm() == 0:
+            assert err < 1e-6, (v.name, err)
+        else:
+            assert err < max(1e-3, 5 * rel_err(i32['grads'][v.name], ref)), (v.name, err)

@@ -63,7 +63,8 @@ def test_flag_names_match_reference_source():
 
 @pytest.mark.parametrize('kw', [dict(resnet_depth=18, image_size=64), dict(resnet_depth=50), dict(resnet_depth=50, width_multiplier=2),
                                 dict(resnet_depth=34, image_size=32, global_bn=False),
-                                dict(resnet_depth=50, sk_ratio=0.0625, image_size=64), dict(resnet_depth=152, width_multiplier=2, sk_ratio=0.0625)])
+                                dict(resnet_depth=50, sk_ratio=0.0625, image_size=64), dict(resnet_depth=152, width_multiplier=2, sk_ratio=0.0625),
+                                dict(resnet_depth=18, se_ratio=0.0625, image_size=64), dict(resnet_depth=50, se_ratio=0.25, sk_ratio=0.0625)])
 def test_variable_inventory_matches_oracle(flags, kw):
     from simclr_b200 import resnet, model, engine
     from oracle import model as OM
