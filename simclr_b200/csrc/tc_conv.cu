@@ -116,6 +116,7 @@ __device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, c
 
 struct SmemCtl {
   uint64_t* full; uint64_t* empty; uint64_t* tmem_full; uint64_t* tmem_empty; uint32_t* tmem_ptr;
+  uint64_t* sfull; uint64_t* sfree;   // staging tile handed to / returned by the statistics warps
   uint8_t* epi;     // 2 x [128][128 B] staging tiles for the TMA-store epilogue
 };
 template <int STAGES>
@@ -124,7 +125,8 @@ __device__ __forceinline__ SmemCtl carve(uint8_t* base, int stage_bytes) {
   c.epi = base + (size_t)STAGES * stage_bytes;
   uint64_t* b = reinterpret_cast<uint64_t*>(c.epi + 2 * A_STAGE_BYTES);
   c.full = b; c.empty = b + STAGES; c.tmem_full = b + 2 * STAGES; c.tmem_empty = b + 2 * STAGES + 2;
-  c.tmem_ptr = reinterpret_cast<uint32_t*>(b + 2 * STAGES + 4);
+  c.sfull = b + 2 * STAGES + 4; c.sfree = b + 2 * STAGES + 6;
+  c.tmem_ptr = reinterpret_cast<uint32_t*>(b + 2 * STAGES + 8);
   return c;
 }
 
@@ -132,7 +134,7 @@ __device__ __forceinline__ SmemCtl carve(uint8_t* base, int stage_bytes) {
 // fprop / dgrad / dense:  out[M][n_out] = gather(src)[M][K] * Wk[n_out][K]^T
 // ===========================================================================
 template <typename T, typename To, int BN, bool A_TMA, bool SMALLC, bool TMA_EPI, bool STATS>
-__global__ void __launch_bounds__(A_TMA ? 192 : 320, 1)
+__global__ void __launch_bounds__((A_TMA && !STATS) ? 192 : 320, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_out, const Geom g, double* __restrict__ bn_sums) {
   using TL = Tile<BN>;
@@ -153,6 +155,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       mbar_init(&ctl.empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.sfull[a], 1); mbar_init(&ctl.sfree[a], GATHER_THREADS); }
     fence_barrier_init();
   }
   if (warp == 5 && lane == 0) {
@@ -160,6 +163,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     if (A_TMA) tma_prefetch_desc(&tmap_a);
     if (TMA_EPI) tma_prefetch_desc(&tmap_out);
   }
+  // With TMA-fed activations warps 6-9 have no gather to do: they take the BatchNorm statistics off the
+  // epilogue's critical path (short-K 1x1 layers are epilogue-bound).
+  constexpr bool STATS_WARPS = STATS && A_TMA;
+  constexpr int BOX_COLS = 128 / (int)sizeof(To);     // 64 (bf16) / 32 (fp32) output columns per staged tile
+  constexpr int BOXES = BN / BOX_COLS;
+  constexpr int CPC = 16 / (int)sizeof(To);           // columns per 16-byte chunk: 8 (bf16) / 4 (fp32)
   if (warp == 4) tmem_alloc(ctl.tmem_ptr, TL::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -174,17 +183,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     if (TMA_EPI) {
       // TMEM -> registers -> 128B-swizzled smem tile [128 rows][128 B] -> TMA store (coalesced,
       // rows >= M and columns >= n_out clipped by the tensor map).  Two staging tiles alternate.
-      constexpr int BOX_COLS = 128 / (int)sizeof(To);     // 64 (bf16) / 32 (fp32) output columns per store
       constexpr int LDS_PER_BOX = BOX_COLS / 32;
-      constexpr int BOXES = BN / BOX_COLS;
-      uint32_t box_ctr = 0;
+      uint32_t box_ctr = 0;                                // counts staged ("live") boxes only
       const int row = warp * 32 + lane;
       // fused BatchNorm statistics (tf2/resnet.py:50-72): per-column sum / sum of squares of the
       // *stored* (rounded) outputs, accumulated in registers over all tiles of this CTA (the host
       // makes gridDim a multiple of tiles_n so a CTA keeps one column block) and flushed once.
       // Thread t owns 16-byte chunk (t & 7) -- CPC consecutive columns -- of rows (t >> 3)*8 .. +7 of
       // every staged tile: 8 conflict-free LDS.128 per box, partial sums kept in registers.
-      constexpr int CPC = 16 / (int)sizeof(To);             // columns per chunk: 8 (bf16) / 4 (fp32)
       const int sj = threadIdx.x & 7, srg = threadIdx.x >> 3;
       float st_sum[BOXES][CPC], st_sq[BOXES][CPC];
 #pragma unroll
@@ -197,12 +203,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         tc_fence_after();
         const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-        for (int b = 0; b < BOXES; ++b, ++box_ctr) {
+        for (int b = 0; b < BOXES; ++b) {
           uint8_t* stage = ctl.epi + (box_ctr & 1) * A_STAGE_BYTES;
           const int n0 = tn * BN + b * BOX_COLS;
           const bool live = n0 < g.n_out;                 // uniform across the CTA
           if (live) {
-            if (threadIdx.x == 0) tma_store_wait_read<1>();   // the store issued two boxes ago has read its tile
+            if (threadIdx.x == 0) {
+              tma_store_wait_read<1>();   // the store issued two boxes ago has read its tile
+              if (STATS_WARPS) mbar_wait(&ctl.sfree[box_ctr & 1], ((box_ctr >> 1) & 1) ^ 1, 11);   // ... and so have the stats warps
+            }
             named_barrier_sync(1, EPI_THREADS);
           }
           const uint32_t srow = smem_u32(stage);
@@ -234,8 +243,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           if (live) {
             fence_proxy_async();
             named_barrier_sync(1, EPI_THREADS);
-            if (threadIdx.x == 0) { tma_store_2d(&tmap_out, stage, n0, tm * 128); tma_store_commit(); }
-            if (STATS) {
+            if (threadIdx.x == 0) {
+              tma_store_2d(&tmap_out, stage, n0, tm * 128); tma_store_commit();
+              if (STATS_WARPS) mbar_arrive(&ctl.sfull[box_ctr & 1]);
+            }
+            if (STATS && !STATS_WARPS) {
               float a0[CPC], a1[CPC];
 #pragma unroll
               for (int c = 0; c < CPC; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
@@ -260,11 +272,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                   for (int c = 0; c < CPC; ++c) { st_sum[bb][c] += a0[c]; st_sq[bb][c] += a1[c]; }
                 }
             }
+            ++box_ctr;
           }
         }
         as ^= 1; if (as == 0) aphase ^= 1;
       }
-      if (STATS) {
+      if (STATS && !STATS_WARPS) {
         const int tn0 = blockIdx.x % g.tiles_n;            // constant for this CTA (gridDim % tiles_n == 0)
 #pragma unroll
         for (int b = 0; b < BOXES; ++b) {
@@ -360,6 +373,57 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
     __syncwarp();
   } else {
+    // ------------------------------ statistics warps (TMA-fed kernels) -----
+    if (STATS_WARPS) {
+      const int st_t = threadIdx.x - 192;
+      const int sj = st_t & 7, srg = st_t >> 3;
+      float st_sum[BOXES][CPC], st_sq[BOXES][CPC];
+#pragma unroll
+      for (int b = 0; b < BOXES; ++b)
+#pragma unroll
+        for (int c = 0; c < CPC; ++c) { st_sum[b][c] = 0.f; st_sq[b][c] = 0.f; }
+      uint32_t ctr = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tn = tile % g.tiles_n;
+#pragma unroll
+        for (int b = 0; b < BOXES; ++b) {
+          if (tn * BN + b * BOX_COLS >= g.n_out) continue;
+          const uint8_t* stage = ctl.epi + (ctr & 1) * A_STAGE_BYTES;
+          mbar_wait(&ctl.sfull[ctr & 1], (ctr >> 1) & 1, 45);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {                     // rows srg*8 + i (rows >= M hold exact zeros)
+            const uint4 raw = *reinterpret_cast<const uint4*>(stage + (srg * 8 + i) * 128 + ((sj ^ i) << 4));
+            float v[CPC];
+            if (sizeof(To) == 2) {
+              const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { v[(2 * e) % CPC] = __uint_as_float(w[e] << 16); v[(2 * e + 1) % CPC] = __uint_as_float(w[e] & 0xffff0000u); }
+            } else {
+              v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2 % CPC] = __uint_as_float(raw.z); v[3 % CPC] = __uint_as_float(raw.w);
+            }
+#pragma unroll
+            for (int c = 0; c < CPC; ++c) { st_sum[b][c] += v[c]; st_sq[b][c] = fmaf(v[c], v[c], st_sq[b][c]); }
+          }
+          mbar_arrive(&ctl.sfree[ctr & 1]);
+          ++ctr;
+        }
+      }
+      const int tn0 = blockIdx.x % g.tiles_n;
+#pragma unroll
+      for (int b = 0; b < BOXES; ++b) {
+#pragma unroll
+        for (int c = 0; c < CPC; ++c) {
+          float s0 = st_sum[b][c], s1 = st_sq[b][c];
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          const int col = tn0 * BN + b * BOX_COLS + sj * CPC + c;
+          if (lane < 8 && col < g.n_out && (int)blockIdx.x < num_tiles) {
+            atomicAdd(bn_sums + col, (double)s0);
+            atomicAdd(bn_sums + g.n_out + col, (double)s1);
+          }
+        }
+      }
+    }
     // ------------------------------ gather producers ----------------------
     // cp.async keeps GATHER_DEPTH K blocks of loads in flight per thread; a stage is handed to the
     // MMA warp (fence.proxy.async + mbarrier arrive) once its group has landed.
@@ -719,7 +783,7 @@ int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
     grid = grid / g.tiles_n * g.tiles_n;
     if (grid < g.tiles_n) grid = g.tiles_n;
   }
-  kern<<<grid, A_TMA ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(ta, tb, tout, g, bn_sums);
+  kern<<<grid, (A_TMA && !STATS) ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(ta, tb, tout, g, bn_sums);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
