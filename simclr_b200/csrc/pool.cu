@@ -43,8 +43,18 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restri
     Vec16<T> o; o.pack(best);
     const int64_t ooff = ((n * Ho + ho) * Wo + wo) * (int64_t)C + c;
     o.store(y + ooff);
+    // V argmax codes packed into one 4/8-byte store (ooff is a multiple of V)
+    if (V == 8) {
+      uint64_t pk = 0;
 #pragma unroll
-    for (int i = 0; i < V; ++i) argmax[ooff + i] = (uint8_t)arg[i];
+      for (int i = 0; i < V; ++i) pk |= (uint64_t)(arg[i] & 0xff) << (8 * i);
+      *reinterpret_cast<uint64_t*>(argmax + ooff) = pk;
+    } else {
+      uint32_t pk = 0;
+#pragma unroll
+      for (int i = 0; i < V; ++i) pk |= (uint32_t)(arg[i] & 0xff) << (8 * i);
+      *reinterpret_cast<uint32_t*>(argmax + ooff) = pk;
+    }
   }
 }
 
@@ -81,8 +91,11 @@ maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ argmax,
         Vec16<T> g; g.load(dy + ooff);
         float f[V]; g.unpack(f);
         const int code = dh * 3 + dw;
+        uint64_t pk;
+        if (V == 8) pk = *reinterpret_cast<const uint64_t*>(argmax + ooff);
+        else pk = *reinterpret_cast<const uint32_t*>(argmax + ooff);
 #pragma unroll
-        for (int i = 0; i < V; ++i) if (argmax[ooff + i] == code) acc[i] += f[i];
+        for (int i = 0; i < V; ++i) if ((int)((pk >> (8 * i)) & 0xff) == code) acc[i] += f[i];
       }
     }
     Vec16<T> o; o.pack(acc);
