@@ -153,14 +153,25 @@ SIMCLR_API int simclr_bn_bwd_reduce(void* dz, const void* dz2, const void* relu_
                                     const void* y, int y_dtype, int64_t rows, int64_t C, const float* mean,
                                     const float* rstd, double* sums, void* stream);
 
+/* Backward, phase 1 of a BN + ReLU without residual (tf2/resnet.py:75-77): the ReLU
+ * mask [scale*y + shift > 0] is recomputed from the saved conv output y, so dz is read
+ * once and never rewritten.  sums as above, over dz*mask. */
+SIMCLR_API int simclr_bn_bwd_relu_reduce(const void* dz, int dtype, const void* y, int y_dtype,
+                                         int64_t rows, int64_t C, const float* mean, const float* rstd,
+                                         const float* scale, const float* shift, double* sums,
+                                         void* stream);
+
 /* Backward, phase 2.  dy = gamma*rstd*(dz - S0/count - xhat*S1/count) with
  * the (all-reduced) sums; dgamma/dbeta (nullable) are written from
- * sums_local (this replica's contribution, summed later with the other grads). */
+ * sums_local (this replica's contribution, summed later with the other grads).
+ * mask_scale / mask_shift (nullable, together): dz is masked on the fly with
+ * [mask_scale*y + mask_shift > 0] (pairs with simclr_bn_bwd_relu_reduce). */
 SIMCLR_API int simclr_bn_bwd_apply(const void* dz, int dtype, const void* y, int y_dtype, void* dy,
                                    int dy_dtype, int64_t rows, int64_t C, const float* mean,
                                    const float* rstd, const float* gamma, const double* sums,
                                    const double* sums_local, double count, float* dgamma, float* dbeta,
-                                   float* coef_ws /* scratch [3][C] */, void* stream);
+                                   float* coef_ws /* scratch [3][C] */, const float* mask_scale,
+                                   const float* mask_shift, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Pooling  (tf2/resnet.py:605-611 MaxPooling2D(3,2,'SAME'); :693-696 mean)

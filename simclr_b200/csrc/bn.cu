@@ -26,7 +26,21 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
   Vec16<__nv_bfloat16> v; v.pack(f); v.store(p);
 }
 
-// Thread layout shared by the two reduction kernels: P threads span the
+// Eight consecutive channels kept in their storage format until they are consumed, so that
+// several rows of loads can be in flight per thread without eight fp32 registers per load.
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void ld(const float* p) { a = reinterpret_cast<const float4*>(p)[0]; b = reinterpret_cast<const float4*>(p)[1]; }
+  __device__ __forceinline__ void to(float* f) const { f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w; }
+};
+template <> struct Raw8<__nv_bfloat16> {
+  Vec16<__nv_bfloat16> v;
+  __device__ __forceinline__ void ld(const __nv_bfloat16* p) { v.load(p); }
+  __device__ __forceinline__ void to(float* f) const { v.unpack(f); }
+};
+
+// Thread layout shared by the reduction kernels: P threads span the
 // channel vectors of a row (power of two <= 256), 256/P "row lanes".
 struct RedLayout { int P, row_lanes, col_iters; };
 inline RedLayout red_layout(int64_t C) {
@@ -38,73 +52,131 @@ inline RedLayout red_layout(int64_t C) {
 }
 
 // mode 0: stats (sum x, sum x^2).  mode 1: bwd reduce (sum dz, sum dz*xhat) with
-// optional in-place dz <- (dz + dz2) * [z > 0].
+// optional in-place dz <- (dz + dz2) * [z > 0].  mode 2: bwd reduce of a BN+ReLU
+// without residual: the mask [scale*y + shift > 0] is recomputed from y (a2 = scale,
+// zmask = shift, both fp32 [C]); dz is neither re-read from a mask tensor nor written.
+// The kernels are HBM-latency bound: each thread keeps 4 (modes 0, 2) or 2 (mode 1) rows of
+// 16-byte loads in flight, two 256-thread CTAs per SM.
 template <typename T, typename Ty, int MODE>
-__global__ void __launch_bounds__(BT)
-bn_reduce_kernel(T* __restrict__ a, const T* __restrict__ a2, const T* __restrict__ zmask,
+__global__ void __launch_bounds__(BT, 2)
+bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __restrict__ zmask_,
                  const Ty* __restrict__ y, int64_t rows, int C, int P, int rows_per_block,
                  const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ sums) {
   extern __shared__ float sh[];   // [row_lanes][P*8][2]
+  const T* __restrict__ a2 = MODE == 2 ? nullptr : (const T*)a2_;
+  const T* __restrict__ zmask = MODE == 2 ? nullptr : (const T*)zmask_;
   const int tx = threadIdx.x % P, ty = threadIdx.x / P;
   const int row_lanes = BT / P;
   const int cvecs = C / 8;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
+  const int64_t lane_step = (int64_t)row_lanes * C;
   for (int cv = tx; cv < cvecs + (P - 1 - ((cvecs - 1) % P)); cv += P) {   // uniform trip count across tx
     const bool active = cv < cvecs;
-    float s0[8], s1[8], mu[8], rs[8];
+    float s0[8], s1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = 0.f; mu[i] = 0.f; rs[i] = 1.f; }
-    if (MODE == 1 && active) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { mu[i] = mean[cv * 8 + i]; rs[i] = rstd[cv * 8 + i]; }
-    }
+    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = 0.f; }
     if (active) {
+      int64_t r = r0 + ty;
       if (MODE == 0) {
-        for (int64_t r = r0 + ty; r < r1; r += row_lanes) {
-          float v[8];
-          load8<T>(a + r * C + (int64_t)cv * 8, v);
+        auto acc = [&](const Raw8<T>& q) {
+          float v[8]; q.to(v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) { s0[i] += v[i]; s1[i] = fmaf(v[i], v[i], s1[i]); }
+        };
+        for (; r + 3 * row_lanes < r1; r += 4 * row_lanes) {
+          const T* p = a + r * C + (int64_t)cv * 8;
+          Raw8<T> q[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) q[u].ld(p + u * lane_step);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc(q[u]);
         }
+        for (; r < r1; r += row_lanes) { Raw8<T> q; q.ld(a + r * C + (int64_t)cv * 8); acc(q); }
+      } else if (MODE == 2) {
+        float mu[8], msc[8], msh[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          mu[i] = mean[cv * 8 + i];
+          msc[i] = ((const float*)a2_)[cv * 8 + i];
+          msh[i] = ((const float*)zmask_)[cv * 8 + i];
+        }
+        // s1 accumulates dz*(y - mean); rstd is applied once at the end
+        auto acc = [&](const Raw8<T>& qg, const Raw8<Ty>& qy) {
+          float g[8], yy[8]; qg.to(g); qy.to(yy);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float gm = fmaf(yy[i], msc[i], msh[i]) > 0.f ? g[i] : 0.f;
+            s0[i] += gm;
+            s1[i] = fmaf(gm, yy[i] - mu[i], s1[i]);
+          }
+        };
+        for (; r + 3 * row_lanes < r1; r += 4 * row_lanes) {
+          const int64_t off = r * C + (int64_t)cv * 8;
+          Raw8<T> qg[4]; Raw8<Ty> qy[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { qg[u].ld(a + off + u * lane_step); qy[u].ld(y + off + u * lane_step); }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc(qg[u], qy[u]);
+        }
+        for (; r < r1; r += row_lanes) {
+          const int64_t off = r * C + (int64_t)cv * 8;
+          Raw8<T> qg; Raw8<Ty> qy; qg.ld(a + off); qy.ld(y + off); acc(qg, qy);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s1[i] *= rstd[cv * 8 + i];
       } else {
-        // two rows per iteration: all loads of both rows are issued before any arithmetic
-        for (int64_t r = r0 + ty; r < r1; r += 2 * row_lanes) {
-          const int64_t off0 = r * C + (int64_t)cv * 8;
-          const bool has1 = r + row_lanes < r1;
-          const int64_t off1 = has1 ? (r + row_lanes) * C + (int64_t)cv * 8 : off0;
-          float v[2][8], w[2][8], z[2][8], yy[2][8];
-          load8<T>(a + off0, v[0]); load8<T>(a + off1, v[1]);
-          if (a2 != nullptr) { load8<T>(a2 + off0, w[0]); load8<T>(a2 + off1, w[1]); }
-          if (zmask != nullptr) { load8<T>(zmask + off0, z[0]); load8<T>(zmask + off1, z[1]); }
-          load8<Ty>(y + off0, yy[0]); load8<Ty>(y + off1, yy[1]);
+        float mu[8];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !has1) break;
-            if (a2 != nullptr) {
+        for (int i = 0; i < 8; ++i) mu[i] = mean[cv * 8 + i];
+        const bool has2 = a2 != nullptr, hasz = zmask != nullptr;
+        auto acc = [&](int64_t off, const Raw8<T>& qv, const Raw8<T>& qw, const Raw8<T>& qz, const Raw8<Ty>& qy) {
+          float v[8], yy[8]; qv.to(v); qy.to(yy);
+          if (has2) {
+            float w[8]; qw.to(w);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[u][i] += w[u][i];
-            }
-            if (zmask != nullptr) {
+            for (int i = 0; i < 8; ++i) v[i] += w[i];
+          }
+          if (hasz) {
+            float z[8]; qz.to(z);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[u][i] = (z[u][i] > 0.f) ? v[u][i] : 0.f;
-            }
-            if (a2 != nullptr || zmask != nullptr) {
-              store8<T>(a + (u == 0 ? off0 : off1), v[u]);
-              // keep the sums consistent with what phase 2 will read back
-              if (sizeof(T) == 2) {
+            for (int i = 0; i < 8; ++i) v[i] = (z[i] > 0.f) ? v[i] : 0.f;
+          }
+          if (has2 || hasz) {
+            store8<T>(a + off, v);
+            // keep the sums consistent with what phase 2 will read back
+            if (sizeof(T) == 2) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[u][i] = to_f<T>(from_f<T>(v[u][i]));
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float xh = (yy[u][i] - mu[i]) * rs[i];
-              s0[i] += v[u][i];
-              s1[i] = fmaf(v[u][i], xh, s1[i]);
+              for (int i = 0; i < 8; ++i) v[i] = to_f<T>(from_f<T>(v[i]));
             }
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s0[i] += v[i]; s1[i] = fmaf(v[i], yy[i] - mu[i], s1[i]); }
+        };
+        for (; r + row_lanes < r1; r += 2 * row_lanes) {
+          const int64_t off = r * C + (int64_t)cv * 8;
+          Raw8<T> qv[2], qw[2], qz[2]; Raw8<Ty> qy[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            qv[u].ld(a + off + u * lane_step);
+            if (has2) qw[u].ld(a2 + off + u * lane_step); else qw[u] = qv[u];
+            if (hasz) qz[u].ld(zmask + off + u * lane_step); else qz[u] = qv[u];
+            qy[u].ld(y + off + u * lane_step);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) acc(off + u * lane_step, qv[u], qw[u], qz[u], qy[u]);
         }
+        for (; r < r1; r += row_lanes) {
+          const int64_t off = r * C + (int64_t)cv * 8;
+          Raw8<T> qv, qw, qz; Raw8<Ty> qy;
+          qv.ld(a + off);
+          if (has2) qw.ld(a2 + off); else qw = qv;
+          if (hasz) qz.ld(zmask + off); else qz = qv;
+          qy.ld(y + off);
+          acc(off, qv, qw, qz, qy);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s1[i] *= rstd[cv * 8 + i];
       }
     }
     // block tree over row lanes
@@ -146,23 +218,24 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
   if (mv) mv[c] = mv[c] - (mv[c] - vf) * (1.f - momentum);
 }
 
+// The host sizes the grid so that gridDim*BT*8 is a multiple of C whenever it can: a thread then
+// stays on one block of 8 channels for the whole grid-stride loop and keeps its per-channel
+// coefficients in registers (reloading them per vector makes these kernels L1-bound).
 template <typename Ty, typename Tz>
 __global__ void __launch_bounds__(BT)
 bn_apply_kernel(const Ty* __restrict__ y, const Tz* __restrict__ res, Tz* __restrict__ z, int64_t nvec, int C,
                 const float* __restrict__ scale, const float* __restrict__ shift, int relu) {
-  for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * BT) {
-    const int64_t off = i * 8;
-    const int c = (int)(off % C);
-    float v[8];
-    load8<Ty>(y + off, v);
-    const float4 sa = *reinterpret_cast<const float4*>(scale + c), sb = *reinterpret_cast<const float4*>(scale + c + 4);
-    const float4 ha = *reinterpret_cast<const float4*>(shift + c), hb = *reinterpret_cast<const float4*>(shift + c + 4);
-    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-    const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+  const int64_t stride = (int64_t)gridDim.x * BT;
+  int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
+  const bool fixed_c = (stride * 8) % C == 0;
+  float sc[8], sh[8];
+  if (fixed_c) { const int c = (int)((i * 8) % C); load8<float>(scale + c, sc); load8<float>(shift + c, sh); }
+  auto body = [&](int64_t off, const Raw8<Ty>& qy, const Raw8<Tz>& qr) {
+    float v[8]; qy.to(v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
     if (res != nullptr) {
-      float r[8]; load8<Tz>(res + off, r);
+      float r[8]; qr.to(r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] += r[k];
     }
@@ -171,6 +244,23 @@ bn_apply_kernel(const Ty* __restrict__ y, const Tz* __restrict__ res, Tz* __rest
       for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
     }
     store8<Tz>(z + off, v);
+  };
+  if (fixed_c) {
+    for (; i + stride < nvec; i += 2 * stride) {
+      const int64_t o0 = i * 8, o1 = (i + stride) * 8;
+      Raw8<Ty> q0, q1; Raw8<Tz> r0, r1;
+      q0.ld(y + o0); q1.ld(y + o1);
+      if (res != nullptr) { r0.ld(res + o0); r1.ld(res + o1); }
+      body(o0, q0, r0); body(o1, q1, r1);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    const int64_t off = i * 8;
+    if (!fixed_c) { const int c = (int)(off % C); load8<float>(scale + c, sc); load8<float>(shift + c, sh); }
+    Raw8<Ty> q; Raw8<Tz> r;
+    q.ld(y + off);
+    if (res != nullptr) r.ld(res + off);
+    body(off, q, r);
   }
 }
 
@@ -193,29 +283,59 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ mean, const float* 
   if (dgamma) dgamma[c] = (float)sums_local[C + c];
 }
 
-template <typename T, typename Ty, typename Td>
+// mask_scale / mask_shift non-null: dz is the gradient w.r.t. relu(scale*y + shift) and the
+// mask is recomputed here instead of being applied to dz in memory beforehand.
+template <typename T, typename Ty, typename Td, bool MASK>
 __global__ void __launch_bounds__(BT)
 bn_bwd_apply_kernel(const T* __restrict__ dz, const Ty* __restrict__ y, Td* __restrict__ dy, int64_t nvec, int C,
-                    const float* __restrict__ coef) {
-  for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * BT) {
-    const int64_t off = i * 8;
-    const int c = (int)(off % C);
-    float g[8], yy[8], o[8], k1[8], k2[8], k3[8];
-    load8<T>(dz + off, g);
-    load8<Ty>(y + off, yy);
-    load8<float>(coef + c, k1);
-    load8<float>(coef + C + c, k2);
-    load8<float>(coef + 2 * C + c, k3);
+                    const float* __restrict__ coef, const float* __restrict__ mask_scale,
+                    const float* __restrict__ mask_shift) {
+  const int64_t stride = (int64_t)gridDim.x * BT;
+  int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
+  const bool fixed_c = (stride * 8) % C == 0;
+  float k1[8], k2[8], k3[8], ms[8], mh[8];
+  auto load_coef = [&](int c) {
+    load8<float>(coef + c, k1); load8<float>(coef + C + c, k2); load8<float>(coef + 2 * C + c, k3);
+    if (MASK) { load8<float>(mask_scale + c, ms); load8<float>(mask_shift + c, mh); }
+  };
+  if (fixed_c) load_coef((int)((i * 8) % C));
+  auto body = [&](int64_t off, const Raw8<T>& qg, const Raw8<Ty>& qy) {
+    float g[8], yy[8], o[8]; qg.to(g); qy.to(yy);
+    if (MASK) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = fmaf(yy[k], ms[k], mh[k]) > 0.f ? g[k] : 0.f;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = fmaf(k1[k], g[k], fmaf(k2[k], yy[k], k3[k]));
     store8<Td>(dy + off, o);
+  };
+  if (fixed_c) {
+    for (; i + stride < nvec; i += 2 * stride) {
+      const int64_t o0 = i * 8, o1 = (i + stride) * 8;
+      Raw8<T> g0, g1; Raw8<Ty> y0, y1;
+      g0.ld(dz + o0); g1.ld(dz + o1); y0.ld(y + o0); y1.ld(y + o1);
+      body(o0, g0, y0); body(o1, g1, y1);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    const int64_t off = i * 8;
+    if (!fixed_c) load_coef((int)(off % C));
+    Raw8<T> qg; Raw8<Ty> qy; qg.ld(dz + off); qy.ld(y + off);
+    body(off, qg, qy);
   }
 }
 
-inline unsigned ew_grid(int64_t nvec) {
+// grid for the element-wise kernels: as many CTAs as fit, rounded down so that gridDim*BT*8 is a
+// multiple of C (see bn_apply_kernel)
+inline unsigned ew_grid_c(int64_t nvec, int64_t C) {
   int64_t b = (nvec + BT - 1) / BT;
   const int64_t cap = (int64_t)num_sms() * 16;
   if (b > cap) b = cap;
+  int64_t q = C, per = (int64_t)BT * 8;          // need b * per % C == 0  <=>  b % (C / gcd(C, per)) == 0
+  int64_t x = q, yv = per;
+  while (yv) { const int64_t t = x % yv; x = yv; yv = t; }
+  const int64_t m = q / x;
+  if (b >= m) b = b / m * m;
   if (b < 1) b = 1;
   return (unsigned)b;
 }
@@ -225,8 +345,8 @@ int launch_reduce(void* a, const void* a2, const void* zmask, const void* y, int
                   const float* mean, const float* rstd, double* sums, cudaStream_t st) {
   const RedLayout l = red_layout(C);
   int64_t nblocks = (rows + l.row_lanes * 8 - 1) / (l.row_lanes * 8);
-  // 3 CTAs of 256 threads are resident per SM (64-74 registers): a multiple of 3*SMs avoids a ragged last wave
-  const int64_t cap = (int64_t)num_sms() * 12;
+  // 2 CTAs of 256 threads are resident per SM (__launch_bounds__(BT, 2)): a multiple of 2*SMs avoids a ragged last wave
+  const int64_t cap = (int64_t)num_sms() * 8;
   if (nblocks > cap) nblocks = cap;
   if (nblocks < 1) nblocks = 1;
   const int rows_per_block = (int)((rows + nblocks - 1) / nblocks);
@@ -235,7 +355,7 @@ int launch_reduce(void* a, const void* a2, const void* zmask, const void* y, int
   cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st);
   if (e != cudaSuccess) { set_error("bn reduce memset: %s", cudaGetErrorString(e)); return (int)e; }
   bn_reduce_kernel<T, Ty, MODE><<<(unsigned)nblocks, BT, smem, st>>>(
-      (T*)a, (const T*)a2, (const T*)zmask, (const Ty*)y, rows, (int)C, l.P, rows_per_block, mean, rstd, sums);
+      (T*)a, a2, zmask, (const Ty*)y, rows, (int)C, l.P, rows_per_block, mean, rstd, sums);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
@@ -277,7 +397,7 @@ int simclr_bn_apply(const void* y, int y_dtype, const void* residual, void* z, i
   SIMCLR_CHECK_ARG(aligned16(y) && aligned16(z) && aligned16(residual), "bn_apply: pointers must be 16-byte aligned");
   const int64_t nvec = rows * C / 8;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = ew_grid(nvec);
+  const unsigned grid = ew_grid_c(nvec, C);
   if (y_dtype == SIMCLR_F32 && z_dtype == SIMCLR_F32)
     bn_apply_kernel<float, float><<<grid, BT, 0, st>>>((const float*)y, (const float*)residual, (float*)z, nvec, (int)C, scale, shift, relu);
   else if (y_dtype == SIMCLR_BF16 && z_dtype == SIMCLR_BF16)
@@ -310,21 +430,46 @@ int simclr_bn_bwd_reduce(void* dz, const void* dz2, const void* relu_mask_z, int
   return SIMCLR_ERR_INVALID_ARG;
 }
 
+int simclr_bn_bwd_relu_reduce(const void* dz, int dtype, const void* y, int y_dtype, int64_t rows, int64_t C,
+                              const float* mean, const float* rstd, const float* scale, const float* shift,
+                              double* sums, void* stream) {
+  SIMCLR_CHECK_ARG(dz && y && mean && rstd && scale && shift && sums, "bn_bwd_relu_reduce: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_bwd_relu_reduce: need rows>0 and C%%8==0");
+  SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(y), "bn_bwd_relu_reduce: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SIMCLR_F32 && y_dtype == SIMCLR_F32)
+    return launch_reduce<float, float, 2>((void*)dz, scale, shift, y, rows, C, mean, rstd, sums, st);
+  if (dtype == SIMCLR_BF16 && y_dtype == SIMCLR_BF16)
+    return launch_reduce<bf16, bf16, 2>((void*)dz, scale, shift, y, rows, C, mean, rstd, sums, st);
+  if (dtype == SIMCLR_BF16 && y_dtype == SIMCLR_F32)
+    return launch_reduce<bf16, float, 2>((void*)dz, scale, shift, y, rows, C, mean, rstd, sums, st);
+  if (dtype == SIMCLR_F32 && y_dtype == SIMCLR_BF16)
+    return launch_reduce<float, bf16, 2>((void*)dz, scale, shift, y, rows, C, mean, rstd, sums, st);
+  set_error("bn_bwd_relu_reduce: unknown dtypes");
+  return SIMCLR_ERR_INVALID_ARG;
+}
+
 int simclr_bn_bwd_apply(const void* dz, int dtype, const void* y, int y_dtype, void* dy, int dy_dtype,
                         int64_t rows, int64_t C, const float* mean, const float* rstd, const float* gamma,
                         const double* sums, const double* sums_local, double count, float* dgamma,
-                        float* dbeta, float* coef_ws, void* stream) {
+                        float* dbeta, float* coef_ws, const float* mask_scale, const float* mask_shift,
+                        void* stream) {
+  SIMCLR_CHECK_ARG((mask_scale == nullptr) == (mask_shift == nullptr), "bn_bwd_apply: mask_scale and mask_shift go together");
   SIMCLR_CHECK_ARG(dz && y && dy && mean && rstd && sums && sums_local && coef_ws, "bn_bwd_apply: null pointer");
   SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && count > 0, "bn_bwd_apply: bad shape");
   SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(y) && aligned16(dy), "bn_bwd_apply: alignment");
   const int64_t nvec = rows * C / 8;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = ew_grid(nvec);
+  const unsigned grid = ew_grid_c(nvec, C);
   SIMCLR_CHECK_ARG(aligned16(coef_ws), "bn_bwd_apply: coef_ws alignment");
   bn_bwd_coef_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(mean, rstd, gamma, sums, sums_local, 1.0 / count,
                                                                    coef_ws, dgamma, dbeta, (int)C);
   SIMCLR_CHECK_LAUNCH();
-#define LAUNCH(T, Ty, Td) bn_bwd_apply_kernel<T, Ty, Td><<<grid, BT, 0, st>>>((const T*)dz, (const Ty*)y, (Td*)dy, nvec, (int)C, coef_ws)
+#define LAUNCH(T, Ty, Td)                                                                                          \
+  do {                                                                                                             \
+    if (mask_scale) bn_bwd_apply_kernel<T, Ty, Td, true><<<grid, BT, 0, st>>>((const T*)dz, (const Ty*)y, (Td*)dy, nvec, (int)C, coef_ws, mask_scale, mask_shift); \
+    else bn_bwd_apply_kernel<T, Ty, Td, false><<<grid, BT, 0, st>>>((const T*)dz, (const Ty*)y, (Td*)dy, nvec, (int)C, coef_ws, nullptr, nullptr); \
+  } while (0)
   const int key = dtype * 4 + y_dtype * 2 + dy_dtype;
   switch (key) {
     case 0: LAUNCH(float, float, float); break;

@@ -74,6 +74,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// im2col-mode load from an NHWC tensor (rank 4: {C, W, H, N}): `pixels-per-column` consecutive base
+// pixels starting at (w, h, n) -- walking W, then H, then N inside the map's bounding box with its
+// traversal stride -- each displaced by the filter offset (off_w, off_h); `channels-per-pixel`
+// channels from c.  Pixels outside the image (padding, n >= N) read as zero.  The smem image is the
+// same [pixel][128 B] 128B-swizzled tile a tiled 2-D box produces.  (Semantics pinned on sm_100a
+// with scripts/probe_im2col.cu.)
+__device__ __forceinline__ void tma_load_im2col(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c, int w,
+                                                int h, int n, int off_w, int off_h) {
+  const uint16_t ow = (uint16_t)off_w, oh = (uint16_t)off_h;
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+      : "memory");
+}
 
 // smem tile -> global through the tensor map (rows/cols outside the tensor are clipped)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
@@ -245,6 +259,47 @@ inline int make_tmap_2d(CUtensorMap* map, const void* base, int elt_bytes, uint6
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu stride=%llu box=%ux%u", (int)r, base,
               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_bytes, box_rows, box_cols);
+    return SIMCLR_ERR_DRIVER;
+  }
+  return SIMCLR_OK;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+inline EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeIm2colFn)p;
+  }
+  return fn;
+}
+
+// im2col map over an NHWC tensor: base pixels lo .. (W-1)+up (same corners for H and W: square
+// filters with symmetric padding only), visited with `trav` (the conv stride); boxes of `pixels`
+// pixels x 128 bytes of channels, 128B swizzle.
+inline int make_tmap_im2col(CUtensorMap* map, const void* base, int elt_bytes, uint64_t N, uint64_t H, uint64_t W,
+                            uint64_t C, int lo, int up, uint32_t trav, uint32_t pixels) {
+  EncodeIm2colFn fn = get_encode_im2col();
+  if (!fn) { set_error("cuTensorMapEncodeIm2col unavailable (no CUDA driver?)"); return SIMCLR_ERR_DRIVER; }
+  const cuuint64_t dims[4] = {C, W, H, N};
+  const cuuint64_t strides[3] = {C * elt_bytes, W * C * elt_bytes, H * W * C * elt_bytes};
+  const int lower[2] = {lo, lo}, upper[2] = {up, up};
+  const cuuint32_t estr[4] = {1, trav, trav, 1};
+  const CUtensorMapDataType dt = elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUresult r = fn(map, dt, 4, const_cast<void*>(base), dims, strides, lower, upper, (cuuint32_t)(128 / elt_bytes),
+                        pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed (%d): base=%p N=%llu H=%llu W=%llu C=%llu corners=%d/%d stride=%u pixels=%u",
+              (int)r, base, (unsigned long long)N, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C,
+              lo, up, trav, pixels);
     return SIMCLR_ERR_DRIVER;
   }
   return SIMCLR_OK;

@@ -50,6 +50,9 @@ struct Geom {
   int tap_sign;        // +1: source = base + (r, s) (fprop / wgrad / tables); -1: base - (r, s) (stride-1 dgrad)
   int tab_r[9], tab_s[9], tab_kcol[9];
   int os, oh0, ow0, OH, OW;
+  // TMA im2col feed of the gathered operand: base pixel of GEMM row (n, p, q) is
+  // (q*stride + im_base, p*stride + im_base); the tap goes into the instruction's filter offsets
+  int im2col, im_base, im_nimg;
 };
 
 template <typename T> struct Elt;
@@ -359,11 +362,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       Pipe pp{0, 0};
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / g.tiles_n, tn = tile - tm * g.tiles_n;
+        // im2col feed: base pixel of the tile's first row; taps advance in K order, cblocks channel blocks each
+        int im_n = 0, im_w = 0, im_h = 0, tap = 0, cb = 0, tr = 0, ts = 0;
+        if (A_TMA && g.im2col) {
+          uint32_t n, rem, p, q;
+          g.dPQ.divmod((uint32_t)(tm * 128), n, rem);
+          g.dQ.divmod(rem, p, q);
+          im_n = (int)n; im_w = (int)q * g.stride + g.im_base; im_h = (int)p * g.stride + g.im_base;
+        }
         for (int kb = 0; kb < g.num_kb; ++kb) {
           mbar_wait(&ctl.empty[pp.stage], pp.phase ^ 1, 30);
           uint8_t* a_dst = smem + (size_t)pp.stage * TL::STAGE_BYTES;
           mbar_arrive_expect_tx(&ctl.full[pp.stage], TL::B_STAGE_BYTES + (A_TMA ? A_STAGE_BYTES : 0));
-          if (A_TMA) tma_load_2d(a_dst, &tmap_a, &ctl.full[pp.stage], kb * KBE, tm * 128);
+          if (A_TMA) {
+            if (g.im2col) {
+              int ow, oh;
+              if (g.use_tab) { ow = g.tab_s[tap] - g.im_base; oh = g.tab_r[tap] - g.im_base; }
+              else if (g.tap_sign > 0) { ow = ts; oh = tr; }
+              else { ow = g.S - 1 - ts; oh = g.R - 1 - tr; }
+              tma_load_im2col(a_dst, &tmap_a, &ctl.full[pp.stage], cb * KBE, im_w, im_h, im_n, ow, oh);
+              if (++cb == g.cblocks) { cb = 0; ++tap; if (++ts == g.S) { ts = 0; ++tr; } }
+            } else {
+              tma_load_2d(a_dst, &tmap_a, &ctl.full[pp.stage], kb * KBE, tm * 128);
+            }
+          }
           int kcol = kb * KBE;
           if (g.use_tab) { const int t = kb / g.cblocks; kcol = g.tab_kcol[t] + (kb - t * g.cblocks) * KBE; }
           tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &ctl.full[pp.stage], kcol, tn * BN);
@@ -652,10 +674,26 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
           uint8_t* a_dst = smem + (size_t)pp.stage * TL::STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_STAGE_BYTES;
           mbar_arrive_expect_tx(&ctl.full[pp.stage], TL::B_STAGE_BYTES + (A_TMA ? A_STAGE_BYTES : 0));
-          if (A_TMA) {     // 1x1 stride-1: the activation tile is a plain [pixels][channels] box
+          if (A_TMA) {
+            if (g.im2col) {  // one im2col column of PXS pixels per atom: the atom's tap is the filter offset
+              uint32_t n, rem, p, q;
+              g.dPQ.divmod((uint32_t)(kb * PXS), n, rem);
+              g.dQ.divmod(rem, p, q);
 #pragma unroll
-            for (int a = 0; a < A_ATOMS; ++a)
-              tma_load_2d(a_dst + a * ATOM_BYTES, &tmap_x, &ctl.full[pp.stage], tk * 128 + a * ATOM_E, kb * PXS);
+              for (int a = 0; a < A_ATOMS; ++a) {
+                uint32_t tap, c, r, s2;
+                g.dC.divmod((uint32_t)(tk * 128 + a * ATOM_E), tap, c);
+                g.dS.divmod(tap, r, s2);
+                const bool live = (int)tap < g.RS;     // k-rows past R*S*C: read a non-existent image (zeros)
+                tma_load_im2col(a_dst + a * ATOM_BYTES, &tmap_x, &ctl.full[pp.stage], (int)c,
+                                (int)q * g.stride + g.im_base, (int)p * g.stride + g.im_base,
+                                live ? (int)n : g.im_nimg, live ? (int)s2 : 0, live ? (int)r : 0);
+              }
+            } else {         // 1x1 stride-1: the activation tile is a plain [pixels][channels] box
+#pragma unroll
+              for (int a = 0; a < A_ATOMS; ++a)
+                tma_load_2d(a_dst + a * ATOM_BYTES, &tmap_x, &ctl.full[pp.stage], tk * 128 + a * ATOM_E, kb * PXS);
+            }
           }
 #pragma unroll
           for (int a = 0; a < B_ATOMS; ++a)
@@ -810,6 +848,37 @@ int dispatch_igemm(int bn, bool a_tma, bool smallc, bool tma_epi, const CUtensor
   return dispatch_igemm2<T, To, 64>(a_tma, smallc, tma_epi, ta, tb, tout, g, bn_sums, st);
 }
 
+// TMA im2col applicability and bounding-box corners for a gathered tensor [N][Hs][Ws][Cs] whose
+// GEMM rows are the P x Q pixel grid.  mode 0: source pixel = p*stride - pad + r (fprop, wgrad);
+// mode 1: p + pad - r (stride-1 dgrad), expressed as base p + pad - (R-1) and offset R-1-r.
+// Base pixels run lo .. (W-1)+up with the traversal stride: exactly Q (P) positions per row (image).
+// SIMCLR_TC_IM2COL=0 forces the cp.async gather (A/B testing).
+struct Im2colPlan { int lo, up; };
+inline bool im2col_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SIMCLR_TC_IM2COL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+inline bool plan_im2col(int mode, int64_t Hs, int64_t Ws, int64_t Cs, int64_t P, int64_t Q, int64_t R, int64_t S,
+                        int64_t stride, int kbe, Im2colPlan* pl) {
+  if (!im2col_enabled() || R != S || Cs % kbe != 0 || stride > 8 || get_encode_im2col() == nullptr) return false;
+  const int pad = (int)((R - 1) / 2);
+  int lo, up_w, up_h;
+  if (mode == 0) {
+    lo = -pad;
+    up_w = (int)(lo + stride * (Q - 1) - (Ws - 1));
+    up_h = (int)(lo + stride * (P - 1) - (Hs - 1));
+  } else {
+    if (stride != 1 || P != Hs || Q != Ws) return false;
+    lo = pad - (int)(R - 1);
+    up_w = up_h = lo;
+  }
+  if (up_w != up_h || lo < -128 || lo > 127 || up_w < -128 || up_w > 127) return false;
+  if (R - 1 > 255 || Hs >= 32768 || Ws >= 32768) return false;
+  pl->lo = lo; pl->up = up_w;
+  return true;
+}
+
 // Shared driver for fprop (mode 0) and dgrad (mode 1).
 //   gathered tensor [N][Hs][Ws][Cs]; GEMM rows = N*P*Q; weights wk [n_out][Kp]
 int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, int out_dtype, int64_t N, int64_t Hs,
@@ -836,13 +905,24 @@ int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, i
   g.Cin = g.Cout = 0; g.splits = 1; g.kb_per_split = g.num_kb;
   g.use_tab = 0; g.cblocks = 1; g.os = 0; g.oh0 = g.ow0 = 0; g.OH = g.OW = 0;
   g.tap_sign = mode == 0 ? 1 : -1;
+  g.im2col = 0; g.im_base = 0; g.im_nimg = (int)N;
   // plain GEMM (1x1, stride 1, no padding): activations go through TMA as well
-  const bool a_tma = (R == 1 && S == 1 && stride == 1 && !smallc && (Cs * es) % 16 == 0);
+  bool a_tma = (R == 1 && S == 1 && stride == 1 && !smallc && (Cs * es) % 16 == 0);
   CUtensorMap ta, tb, tout;
   int rc = make_tmap_2d(&tb, wk, es, (uint64_t)n_out, (uint64_t)Kp, (uint64_t)Kp * es, (uint32_t)bn, (uint32_t)KBE);
   if (rc) return rc;
   if (a_tma) { rc = make_tmap_2d(&ta, src, es, (uint64_t)M, (uint64_t)Cs, (uint64_t)Cs * es, 128, (uint32_t)KBE); if (rc) return rc; }
-  else ta = tb;
+  else {
+    ta = tb;
+    // every other shape with whole 128-byte channel blocks: TMA im2col (square filter, symmetric padding)
+    Im2colPlan pl;
+    if (!smallc && plan_im2col(mode, Hs, Ws, Cs, P, Q, R, S, stride, KBE, &pl)) {
+      rc = make_tmap_im2col(&ta, src, es, (uint64_t)N, (uint64_t)Hs, (uint64_t)Ws, (uint64_t)Cs, pl.lo, pl.up, (uint32_t)stride, 128);
+      if (rc) return rc;
+      g.im2col = 1; g.im_base = pl.lo; g.cblocks = (int)(Cs / KBE);
+      a_tma = true;
+    }
+  }
   // coalesced TMA-store epilogue whenever the output rows are 16-byte aligned
   const int eo = out_dtype == SIMCLR_BF16 ? 2 : 4;
   const bool tma_epi = aligned16(out) && ((n_out * eo) % 16 == 0);
@@ -920,9 +1000,24 @@ int run_dgrad_strided(const void* dy, const void* wd, void* dx, int dtype, int o
       g.Cin = g.Cout = 0; g.splits = 1; g.kb_per_split = g.num_kb;
       g.tap_sign = 1;
       g.use_tab = 1; g.os = (int)stride; g.oh0 = ph; g.ow0 = pw; g.OH = (int)H; g.OW = (int)W;
-      if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_BF16) rc = dispatch_igemm<__nv_bfloat16, __nv_bfloat16>(bn, false, false, false, tb, tb, tb, g, st);
-      else if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_F32) rc = dispatch_igemm<__nv_bfloat16, float>(bn, false, false, false, tb, tb, tb, g, st);
-      else if (dtype == SIMCLR_F32 && out_dtype == SIMCLR_F32) rc = dispatch_igemm<float, float>(bn, false, false, false, tb, tb, tb, g, st);
+      // the class is a stride-1 walk over the dY grid: TMA im2col when its pixel grid is the dY grid
+      g.im2col = 0; g.im_base = 0; g.im_nimg = (int)N;
+      CUtensorMap ta = tb;
+      bool a_tma = false;
+      if (im2col_enabled() && get_encode_im2col() != nullptr && P2 == Ho && Q2 == Wo && Ho < 32768 && Wo < 32768) {
+        int lo = g.tab_r[0];
+        for (int t = 0; t < nt; ++t) { lo = g.tab_r[t] < lo ? g.tab_r[t] : lo; lo = g.tab_s[t] < lo ? g.tab_s[t] : lo; }
+        int hi = lo;
+        for (int t = 0; t < nt; ++t) { hi = g.tab_r[t] > hi ? g.tab_r[t] : hi; hi = g.tab_s[t] > hi ? g.tab_s[t] : hi; }
+        if (lo >= -128 && hi - lo <= 255) {
+          rc = make_tmap_im2col(&ta, dy, es, (uint64_t)N, (uint64_t)Ho, (uint64_t)Wo, (uint64_t)Cout, lo, lo, 1, 128);
+          if (rc) return rc;
+          g.im2col = 1; g.im_base = lo; a_tma = true;
+        }
+      }
+      if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_BF16) rc = dispatch_igemm<__nv_bfloat16, __nv_bfloat16>(bn, a_tma, false, false, ta, tb, tb, g, st);
+      else if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_F32) rc = dispatch_igemm<__nv_bfloat16, float>(bn, a_tma, false, false, ta, tb, tb, g, st);
+      else if (dtype == SIMCLR_F32 && out_dtype == SIMCLR_F32) rc = dispatch_igemm<float, float>(bn, a_tma, false, false, ta, tb, tb, g, st);
       else { set_error("conv2d_dgrad_tc: unsupported dtype combination"); return SIMCLR_ERR_UNSUPPORTED; }
       if (rc) return rc;
     }
@@ -1045,9 +1140,18 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   CUtensorMap tdy, tx;
   int rc = make_tmap_2d(&tdy, dy, es, (uint64_t)M, (uint64_t)Cout, (uint64_t)Cout * es, (uint32_t)pxs, (uint32_t)ATOM_E);
   if (rc) return rc;
-  const bool a_tma = (R == 1 && S == 1 && stride == 1 && !smallc && (Cs * es) % 16 == 0);
+  bool a_tma = (R == 1 && S == 1 && stride == 1 && !smallc && (Cs * es) % 16 == 0);
+  g.im2col = 0; g.im_base = 0; g.im_nimg = (int)N;
   if (a_tma) { rc = make_tmap_2d(&tx, x, es, (uint64_t)M, (uint64_t)Cs, (uint64_t)Cs * es, (uint32_t)pxs, (uint32_t)ATOM_E); if (rc) return rc; }
-  else tx = tdy;
+  else {
+    tx = tdy;
+    Im2colPlan pl;
+    if (!smallc && plan_im2col(0, H, W, Cs, Ho, Wo, R, S, stride, ATOM_E, &pl)) {
+      rc = make_tmap_im2col(&tx, x, es, (uint64_t)N, (uint64_t)H, (uint64_t)W, (uint64_t)Cs, pl.lo, pl.up, (uint32_t)stride, (uint32_t)pxs);
+      if (rc) return rc;
+      g.im2col = 1; g.im_base = pl.lo; a_tma = true;
+    }
+  }
   // splits are combined by TMA reduce-add when dW is a plain [R*S*Cin][Cout] fp32 matrix with 16-byte rows
   CUtensorMap tdw;
   const bool tma_red = !smallc && Cs == Cin && aligned16(dw) && (Cout * 4) % 16 == 0;

@@ -63,21 +63,34 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
         z = e.empty(y.shape, out_dtype or y.dtype)
         lib.bn_apply(y, e.code(y.dtype), residual, z, e.code(z.dtype), rows, C, scale, shift, int(relu), st)
         if training:
-            self.saved = (y, z if relu else None, mean, rstd, rows)
+            # BN+ReLU without residual: the backward recomputes the mask from y (scale, shift)
+            self.saved = (y, z if (relu and residual is not None) else None, mean, rstd, rows,
+                          (scale, shift) if (relu and residual is None) else None)
         return z
 
     def backward(self, dz, dz2=None, dy_dtype=None):
-        """dz (and dz2) are gradients w.r.t. the layer output; dz is overwritten
-        with (dz + dz2) * relu_mask when either applies.  Returns d(inputs)."""
+        """dz (and dz2) are gradients w.r.t. the layer output.  For the block tail
+        (residual add + ReLU) dz is overwritten with (dz + dz2) * relu_mask, which the
+        caller routes on to the shortcut; a plain BN+ReLU leaves dz untouched.
+        Returns d(inputs)."""
         e = get_engine()
-        y, zmask, mean, rstd, rows = self.saved
+        y, zmask, mean, rstd, rows, remask = self.saved
         self.saved = None
         C = self.C
         st = stream_ptr()
         sums = e.empty((2 * C,), torch.float64)
         if zmask is not None:
             assert zmask.dtype == dz.dtype
-        lib.bn_bwd_reduce(dz, dz2, zmask, e.code(dz.dtype), y, e.code(y.dtype), rows, C, mean, rstd, sums, st)
+        if remask is not None and dz2 is None:
+            lib.bn_bwd_relu_reduce(dz, e.code(dz.dtype), y, e.code(y.dtype), rows, C, mean, rstd,
+                                   remask[0], remask[1], sums, st)
+            msc, msh = remask
+        else:
+            if remask is not None:      # extra gradient into a plain BN+ReLU: mask in place from z
+                zmask = e.empty(y.shape, dz.dtype)
+                lib.bn_apply(y, e.code(y.dtype), None, zmask, e.code(zmask.dtype), rows, C, remask[0], remask[1], 1, st)
+            lib.bn_bwd_reduce(dz, dz2, zmask, e.code(dz.dtype), y, e.code(y.dtype), rows, C, mean, rstd, sums, st)
+            msc = msh = None
         sums_g, count = sums, float(rows)
         if e.sync_bn:
             sums_g = sums.clone()
@@ -88,7 +101,7 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
         lib.bn_bwd_apply(dz, e.code(dz.dtype), y, e.code(y.dtype), dy, e.code(dy.dtype), rows, C, mean, rstd,
                          None if self.gamma is None else self.gamma.value, sums_g, sums, count,
                          None if self.gamma is None else self.gamma.grad,
-                         None if self.beta is None else self.beta.grad, coef, st)
+                         None if self.beta is None else self.beta.grad, coef, msc, msh, st)
         return dy
 
 

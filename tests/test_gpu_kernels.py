@@ -223,6 +223,8 @@ def test_batchnorm_fwd_bwd(eng, flags, shape, dtype, relu, residual):
         pass
     dzd = _dev(dz)
     dx = bn.backward(dzd, dy_dtype=dtype)
+    if not residual:
+        assert torch.equal(dzd.cpu(), dz), 'plain BN(+ReLU) backward must not rewrite dz'
     tolb = 2e-4 if dtype == torch.float32 else 2e-2
     assert rel_err(dx, xo.grad) < tolb
     assert rel_err(bn.gamma.grad, P[obn.gamma].grad) < tolb

@@ -28,6 +28,10 @@ CASES = [
     (1, 5, 7, 64, 64, 64, 3, 1),         # tiny M (35 rows)
     (4, 28, 28, 128, 128, 512, 1, 1),    # several tiles per CTA? (M=3136 -> 25 tiles x 2)
     (2, 14, 14, 1024, 1024, 256, 1, 1),  # long K (16 K blocks) through the smem ring
+    (2, 14, 14, 256, 256, 256, 3, 1),    # TMA im2col: four channel blocks per tap, tiles crossing images
+    (3, 9, 9, 64, 64, 64, 3, 2),         # odd extent, strided: im2col fprop/wgrad, dgrad classes of unequal size
+    (2, 12, 12, 64, 64, 128, 3, 2),      # 64-channel strided 3x3 (two taps per 128 k-rows in wgrad)
+    (1, 9, 11, 64, 64, 64, 5, 1),        # 5x5, rectangular image
 ]
 
 
@@ -130,27 +134,30 @@ def test_tc_tf32(case):
         lib.conv2d_wgrad_tc(xs.cuda(), dy.cuda(), dw, 0, N, H, W, Cs, Cin, Cout, k, k, s, st)
 
 
-def test_tc_matches_simt_large():
-    """Size-independent check at a BASELINE-sized layer: tcgen05 vs the CUDA-core
-    engine on the same bf16 inputs (R50 stage-2 3x3, 64 views)."""
+@pytest.mark.parametrize('shape', [(64, 28, 28, 128, 128, 3, 1), (16, 56, 56, 64, 64, 3, 1), (16, 56, 56, 128, 128, 3, 2),
+                                   (16, 28, 28, 256, 512, 1, 2), (8, 56, 56, 64, 256, 1, 1)])
+def test_tc_matches_simt_large(shape):
+    """Size-independent check at BASELINE-sized layers (many tiles per CTA, tiles crossing image
+    rows and images): tcgen05 vs the CUDA-core engine on the same bf16 inputs."""
     from simclr_b200._lib import lib, stream_ptr
-    N, H, W, C, k, s = 64, 28, 28, 128, 3, 1
+    N, H, W, C, Co, k, s = shape
+    Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
     torch.manual_seed(11)
     x = torch.randn(N, H, W, C, device='cuda').to(torch.bfloat16)
-    w = (torch.randn(k, k, C, C, device='cuda') * 0.03).to(torch.bfloat16)
-    dy = torch.randn(N, H, W, C, device='cuda').to(torch.bfloat16)
-    wf, wd = _pack(w.cpu(), torch.bfloat16, k, C, C, C)
+    w = (torch.randn(k, k, C, Co, device='cuda') * 0.03).to(torch.bfloat16)
+    dy = torch.randn(N, Ho, Wo, Co, device='cuda').to(torch.bfloat16)
+    wf, wd = _pack(w.cpu(), torch.bfloat16, k, C, C, Co)
     st = stream_ptr()
     wf32 = w.float().contiguous()
-    y_tc = torch.empty(N, H, W, C, device='cuda'); y_ref = torch.empty_like(y_tc)
-    lib.conv2d_fprop_tc(x, wf, y_tc, 1, 0, N, H, W, C, C, k, k, s, None, st)
-    lib.conv2d_fprop_simt(x, wf32, y_ref, 1, 0, N, H, W, C, C, C, k, k, s, st)
+    y_tc = torch.empty(N, Ho, Wo, Co, device='cuda'); y_ref = torch.empty_like(y_tc)
+    lib.conv2d_fprop_tc(x, wf, y_tc, 1, 0, N, H, W, C, Co, k, k, s, None, st)
+    lib.conv2d_fprop_simt(x, wf32, y_ref, 1, 0, N, H, W, C, C, Co, k, k, s, st)
     dx_tc = torch.empty(N, H, W, C, device='cuda'); dx_ref = torch.empty_like(dx_tc)
-    lib.conv2d_dgrad_tc(dy, wd, dx_tc, 1, 0, N, H, W, C, C, k, k, s, st)
-    lib.conv2d_dgrad_simt(dy, wf32, dx_ref, 1, 0, N, H, W, C, C, k, k, s, st)
-    dw_tc = torch.empty(k, k, C, C, device='cuda'); dw_ref = torch.empty_like(dw_tc)
-    lib.conv2d_wgrad_tc(x, dy, dw_tc, 1, N, H, W, C, C, C, k, k, s, st)
-    lib.conv2d_wgrad_simt(x, dy, dw_ref, 1, N, H, W, C, C, C, k, k, s, st)
+    lib.conv2d_dgrad_tc(dy, wd, dx_tc, 1, 0, N, H, W, C, Co, k, k, s, st)
+    lib.conv2d_dgrad_simt(dy, wf32, dx_ref, 1, 0, N, H, W, C, Co, k, k, s, st)
+    dw_tc = torch.empty(k, k, C, Co, device='cuda'); dw_ref = torch.empty_like(dw_tc)
+    lib.conv2d_wgrad_tc(x, dy, dw_tc, 1, N, H, W, C, C, Co, k, k, s, st)
+    lib.conv2d_wgrad_simt(x, dy, dw_ref, 1, N, H, W, C, C, Co, k, k, s, st)
     torch.cuda.synchronize()
     assert rel_err(y_tc, y_ref) < 2e-4
     assert rel_err(dx_tc, dx_ref) < 2e-4
