@@ -58,48 +58,72 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restri
   }
 }
 
+// One thread per 2x2 block of input pixels and V channels.  With stride 2 and a 3x3 window the
+// block's pixels lie in at most 2x2 pooling windows (ho, wo in {hb - 1 + pb, hb + pb}): their dy and
+// argmax vectors are loaded once and routed to the four pixels.
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ argmax, T* __restrict__ dx,
                    int64_t total, int H, int W, int C, int Ho, int Wo, int pb_h, int pb_w) {
   constexpr int V = Vec16<T>::N;
   const int cv = C / V;
+  const int Hb = (H + 1) / 2, Wb = (W + 1) / 2;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % cv) * V;
     int64_t p = idx / cv;
-    const int w = (int)(p % W); p /= W;
-    const int h = (int)(p % H);
-    const int64_t n = p / H;
-    float acc[V];
+    const int wb = (int)(p % Wb); p /= Wb;
+    const int hb = (int)(p % Hb);
+    const int64_t n = p / Hb;
+    float g[2][2][V];
+    uint64_t am[2][2];
+    bool live[2][2];
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] = 0.f;
-    // windows (ho,wo) with ho*2 - pb + dh == h, dh in 0..2
+    for (int i = 0; i < 2; ++i) {
 #pragma unroll
-    for (int dh = 0; dh < 3; ++dh) {
-      const int t = h + pb_h - dh;
-      if (t < 0 || (t & 1)) continue;
-      const int ho = t >> 1;
-      if (ho >= Ho) continue;
+      for (int j = 0; j < 2; ++j) {
+        const int ho = hb - 1 + pb_h + i, wo = wb - 1 + pb_w + j;
+        live[i][j] = ho >= 0 && ho < Ho && wo >= 0 && wo < Wo;
+        am[i][j] = 0;
+        if (live[i][j]) {
+          const int64_t ooff = ((n * Ho + ho) * Wo + wo) * (int64_t)C + c;
+          Vec16<T> v; v.load(dy + ooff); v.unpack(g[i][j]);
+          if (V == 8) am[i][j] = *reinterpret_cast<const uint64_t*>(argmax + ooff);
+          else am[i][j] = *reinterpret_cast<const uint32_t*>(argmax + ooff);
+        } else {
 #pragma unroll
-      for (int dw = 0; dw < 3; ++dw) {
-        const int u = w + pb_w - dw;
-        if (u < 0 || (u & 1)) continue;
-        const int wo = u >> 1;
-        if (wo >= Wo) continue;
-        const int64_t ooff = ((n * Ho + ho) * Wo + wo) * (int64_t)C + c;
-        Vec16<T> g; g.load(dy + ooff);
-        float f[V]; g.unpack(f);
-        const int code = dh * 3 + dw;
-        uint64_t pk;
-        if (V == 8) pk = *reinterpret_cast<const uint64_t*>(argmax + ooff);
-        else pk = *reinterpret_cast<const uint32_t*>(argmax + ooff);
-#pragma unroll
-        for (int i = 0; i < V; ++i) if ((int)((pk >> (8 * i)) & 0xff) == code) acc[i] += f[i];
+          for (int k = 0; k < V; ++k) g[i][j][k] = 0.f;
+        }
       }
     }
-    Vec16<T> o; o.pack(acc);
-    o.store(dx + (((n * H + h) * W + w) * (int64_t)C + c));
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int h = 2 * hb + a;
+      if (h >= H) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int w = 2 * wb + b;
+        if (w >= W) continue;
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int dh = a + 2 - pb_h - 2 * i;        // h + pb_h - 2*ho with ho = hb - 1 + pb_h + i
+          if (dh < 0 || dh > 2) continue;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int dw = b + 2 - pb_w - 2 * j;
+            if (dw < 0 || dw > 2 || !live[i][j]) continue;
+            const int code = dh * 3 + dw;
+#pragma unroll
+            for (int k = 0; k < V; ++k) if ((int)((am[i][j] >> (8 * k)) & 0xff) == code) acc[k] += g[i][j][k];
+          }
+        }
+        Vec16<T> o; o.pack(acc);
+        o.store(dx + (((n * H + h) * W + w) * (int64_t)C + c));
+      }
+    }
   }
 }
 
@@ -175,10 +199,10 @@ int simclr_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int
   same_pad(H, &Ho, &pbh); same_pad(W, &Wo, &pbw);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SIMCLR_F32) {
-    const int64_t total = N * H * W * (C / 4);
+    const int64_t total = N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
     maxpool_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)dy, argmax, (float*)dx, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw);
   } else if (dtype == SIMCLR_BF16) {
-    const int64_t total = N * H * W * (C / 8);
+    const int64_t total = N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
     maxpool_bwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)dy, argmax, (bf16*)dx, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw);
   } else { set_error("maxpool_bwd: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
   SIMCLR_CHECK_LAUNCH();

@@ -74,6 +74,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// packed fp32 pairs (sm_100 FADD2 / FFMA2): halves the instruction count of the statistics loops
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+
 // im2col-mode load from an NHWC tensor (rank 4: {C, W, H, N}): `pixels-per-column` consecutive base
 // pixels starting at (w, h, n) -- walking W, then H, then N inside the map's bounding box with its
 // traversal stride -- each displaced by the filter offset (off_w, off_h); `channels-per-pixel`

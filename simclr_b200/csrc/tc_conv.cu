@@ -117,6 +117,12 @@ __device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, c
   }
 }
 
+// One arrival per warp: 32 lanes arriving on the same mbarrier serialise in the LSU.
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
 struct SmemCtl {
   uint64_t* full; uint64_t* empty; uint64_t* tmem_full; uint64_t* tmem_empty; uint32_t* tmem_ptr;
   uint64_t* sfull; uint64_t* sfree;   // staging tile handed to / returned by the statistics warps
@@ -154,11 +160,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&ctl.full[s], A_TMA ? 1 : 1 + GATHER_THREADS);
+      mbar_init(&ctl.full[s], A_TMA ? 1 : 1 + GATHER_THREADS / 32);
       mbar_init(&ctl.empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.sfull[a], 1); mbar_init(&ctl.sfree[a], GATHER_THREADS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS / 32); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.sfull[a], 1); mbar_init(&ctl.sfree[a], GATHER_THREADS / 32); }
     fence_barrier_init();
   }
   if (warp == 5 && lane == 0) {
@@ -242,7 +248,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               }
             }
           }
-          if (b == BOXES - 1) { tc_fence_before(); mbar_arrive(&ctl.tmem_empty[as]); }   // accumulator drained
+          if (b == BOXES - 1) { tc_fence_before(); warp_arrive(&ctl.tmem_empty[as]); }   // accumulator drained
           if (live) {
             fence_proxy_async();
             named_barrier_sync(1, EPI_THREADS);
@@ -324,7 +330,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           if (m < g.M && valid > 0) store_row32<To>(out + row_off + n0, acc, valid, vec_ok);
         }
         tc_fence_before();
-        mbar_arrive(&ctl.tmem_empty[as]);
+        warp_arrive(&ctl.tmem_empty[as]);
         as ^= 1; if (as == 0) aphase ^= 1;
       }
     }
@@ -399,11 +405,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     if (STATS_WARPS) {
       const int st_t = threadIdx.x - 192;
       const int sj = st_t & 7, srg = st_t >> 3;
-      float st_sum[BOXES][CPC], st_sq[BOXES][CPC];
+      // packed fp32 pairs: (sum, sum) and (sumsq, sumsq) of two adjacent columns per register pair
+      constexpr int CP2 = CPC / 2;
+      uint64_t st_sum[BOXES][CP2], st_sq[BOXES][CP2];
 #pragma unroll
       for (int b = 0; b < BOXES; ++b)
 #pragma unroll
-        for (int c = 0; c < CPC; ++c) { st_sum[b][c] = 0.f; st_sq[b][c] = 0.f; }
+        for (int c = 0; c < CP2; ++c) { st_sum[b][c] = 0ull; st_sq[b][c] = 0ull; }
       uint32_t ctr = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tn = tile % g.tiles_n;
@@ -415,18 +423,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 8; ++i) {                     // rows srg*8 + i (rows >= M hold exact zeros)
             const uint4 raw = *reinterpret_cast<const uint4*>(stage + (srg * 8 + i) * 128 + ((sj ^ i) << 4));
-            float v[CPC];
             if (sizeof(To) == 2) {
               const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { v[(2 * e) % CPC] = __uint_as_float(w[e] << 16); v[(2 * e + 1) % CPC] = __uint_as_float(w[e] & 0xffff0000u); }
+              for (int e = 0; e < 4; ++e) {
+                const uint64_t v = f2_pack(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+                st_sum[b][e % CP2] = f2_add(st_sum[b][e % CP2], v);
+                st_sq[b][e % CP2] = f2_fma(v, v, st_sq[b][e % CP2]);
+              }
             } else {
-              v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2 % CPC] = __uint_as_float(raw.z); v[3 % CPC] = __uint_as_float(raw.w);
+              const uint64_t v0 = f2_pack(__uint_as_float(raw.x), __uint_as_float(raw.y));
+              const uint64_t v1 = f2_pack(__uint_as_float(raw.z), __uint_as_float(raw.w));
+              st_sum[b][0] = f2_add(st_sum[b][0], v0); st_sq[b][0] = f2_fma(v0, v0, st_sq[b][0]);
+              st_sum[b][1 % CP2] = f2_add(st_sum[b][1 % CP2], v1); st_sq[b][1 % CP2] = f2_fma(v1, v1, st_sq[b][1 % CP2]);
             }
-#pragma unroll
-            for (int c = 0; c < CPC; ++c) { st_sum[b][c] += v[c]; st_sq[b][c] = fmaf(v[c], v[c], st_sq[b][c]); }
           }
-          mbar_arrive(&ctl.sfree[ctr & 1]);
+          warp_arrive(&ctl.sfree[ctr & 1]);
           ++ctr;
         }
       }
@@ -435,7 +447,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       for (int b = 0; b < BOXES; ++b) {
 #pragma unroll
         for (int c = 0; c < CPC; ++c) {
-          float s0 = st_sum[b][c], s1 = st_sq[b][c];
+          float lo0, hi0, lo1, hi1;
+          f2_unpack(st_sum[b][c / 2], lo0, hi0); f2_unpack(st_sq[b][c / 2], lo1, hi1);
+          float s0 = (c & 1) ? hi0 : lo0, s1 = (c & 1) ? hi1 : lo1;
           s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
           s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
           const int col = tn0 * BN + b * BOX_COLS + sj * CPC + c;
@@ -506,7 +520,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           if (++inflight == D) {
             cp_async_wait<D - 1>();
             fence_proxy_async();
-            mbar_arrive(&ctl.full[pa.stage]);
+            warp_arrive(&ctl.full[pa.stage]);
             advance<STAGES>(pa);
             --inflight;
           }
@@ -514,7 +528,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       }
       cp_async_wait<0>();
       fence_proxy_async();
-      for (; inflight > 0; --inflight) { mbar_arrive(&ctl.full[pa.stage]); advance<STAGES>(pa); }
+      for (; inflight > 0; --inflight) { warp_arrive(&ctl.full[pa.stage]); advance<STAGES>(pa); }
     }
   }
 
@@ -551,8 +565,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl.full[s], A_TMA ? 1 : 1 + GATHER_THREADS); mbar_init(&ctl.empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl.full[s], A_TMA ? 1 : 1 + GATHER_THREADS / 32); mbar_init(&ctl.empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS / 32); }
     fence_barrier_init();
   }
   if (warp == 5 && lane == 0) {
@@ -600,7 +614,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
           uint32_t acc[32];
           tmem_ld32(tbase + cc * 32, acc);
           tmem_ld_wait();
-          if (cc == BN / 32 - 1) { tc_fence_before(); mbar_arrive(&ctl.tmem_empty[as]); }
+          if (cc == BN / 32 - 1) { tc_fence_before(); warp_arrive(&ctl.tmem_empty[as]); }
           if (live) {
             const uint32_t srow = smem_u32(stage);
 #pragma unroll
@@ -629,7 +643,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
           }
         }
         tc_fence_before();
-        mbar_arrive(&ctl.tmem_empty[as]);
+        warp_arrive(&ctl.tmem_empty[as]);
       }
       as ^= 1; if (as == 0) aphase ^= 1;
     }
@@ -783,7 +797,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         if (++inflight == D) {
           cp_async_wait<D - 1>();
           fence_proxy_async();
-          mbar_arrive(&ctl.full[pa.stage]);
+          warp_arrive(&ctl.full[pa.stage]);
           advance<STAGES>(pa);
           --inflight;
         }
@@ -791,7 +805,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (; inflight > 0; --inflight) { mbar_arrive(&ctl.full[pa.stage]); advance<STAGES>(pa); }
+    for (; inflight > 0; --inflight) { warp_arrive(&ctl.full[pa.stage]); advance<STAGES>(pa); }
   }
 
   tc_fence_before();
