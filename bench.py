@@ -296,11 +296,28 @@ def run_b200(args):
             d[0] += flops; d[1] += a.elapsed_time(b) * 1e-3; d[2] += 1
         tot_f = sum(v[0] for v in by.values()); tot_t = sum(v[1] for v in by.values())
         achieved = tot_f / tot_t / 1e12 if tot_t > 0 else 0.0
+        # algorithmic bytes of the conv kernels (activations in + out once, packed weights once) and, when the
+        # committed ncu capture matches this workload, the DRAM traffic it measured (profiles/traffic.json)
+        alg = 0.0
+        for kind, shape, flops, a, b in eng.profile:
+            n_, h_, w_, ci, co, r_, s_ = shape
+            ho, wo = (h_ - 1) // s_ + 1, (w_ - 1) // s_ + 1
+            alg += 2.0 * (n_ * h_ * w_ * ci + n_ * ho * wo * co + r_ * r_ * ci * co)
+        n_launch = max(len(eng.profile), 1)
+        traffic = None; traffic_src = None
+        tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic.json')
+        if os.path.exists(tj) and args.resnet_depth == 50 and args.width_multiplier == 1 and B == 512 and S == 224:
+            try:
+                tr = json.load(open(tj))
+                traffic = tr['dram_bytes_per_launch']; traffic_src = 'profiles/traffic.json (%s)' % tr['source']
+            except Exception:
+                traffic = None
         key = (args.resnet_depth, args.width_multiplier, S)
         step_tflops = (ips / world) * GFLOP_PER_IMAGE[key] / 1e3 if key in GFLOP_PER_IMAGE else None
         roof = {'bound': 'tensor', 'kernel': 'igemm_kernel/wgrad_kernel (tcgen05 implicit GEMM, %d launches/step)' % sum(v[2] for v in by.values()),
                 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops'],
-                'traffic': None, 'peak_source': peaks['which'],
+                'traffic': traffic, 'traffic_source': traffic_src, 'algorithmic_bytes': alg / n_launch,
+                'peak_source': peaks['which'],
                 'conv_share_of_step': tot_t * 1e3 / ms_per_step,
                 'conv_kernel_ms': tot_t * 1e3,
                 'by_kind': {k: {'tflops': v[0] / v[1] / 1e12, 'ms': v[1] * 1e3, 'launches': v[2]} for k, v in by.items()},
