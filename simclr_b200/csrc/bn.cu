@@ -345,8 +345,10 @@ int launch_reduce(void* a, const void* a2, const void* zmask, const void* y, int
                   const float* mean, const float* rstd, double* sums, cudaStream_t st) {
   const RedLayout l = red_layout(C);
   int64_t nblocks = (rows + l.row_lanes * 8 - 1) / (l.row_lanes * 8);
-  // 2 CTAs of 256 threads are resident per SM (__launch_bounds__(BT, 2)): a multiple of 2*SMs avoids a ragged last wave
-  const int64_t cap = (int64_t)num_sms() * 8;
+  // 2 CTAs of 256 threads are resident per SM (__launch_bounds__(BT, 2)): one wave of fat blocks.  Every block ends
+  // with one fp64 atomic per column, and same-address atomics serialise in L2 (~30 ns each): 8 waves of blocks
+  // cost ~30 us of atomic tail per launch, one wave a quarter of that.
+  const int64_t cap = (int64_t)num_sms() * 2;
   if (nblocks > cap) nblocks = cap;
   if (nblocks < 1) nblocks = 1;
   const int rows_per_block = (int)((rows + nblocks - 1) / nblocks);

@@ -442,7 +442,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           ++ctr;
         }
       }
+      // Flush: fold the row groups of a warp by shuffles, the four warps through shared memory (the
+      // operand ring is idle by now: every MMA of this CTA has retired), then ONE fp64 atomic per
+      // column per CTA -- same-address atomics serialise in L2 (~30 ns each), so their count per
+      // column, not their total, sets the tail of the kernel.
       const int tn0 = blockIdx.x % g.tiles_n;
+      float* red = reinterpret_cast<float*>(smem);          // [4 warps][BN columns][2]
+      const int sw = st_t >> 5;
 #pragma unroll
       for (int b = 0; b < BOXES; ++b) {
 #pragma unroll
@@ -452,11 +458,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           float s0 = (c & 1) ? hi0 : lo0, s1 = (c & 1) ? hi1 : lo1;
           s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
           s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-          const int col = tn0 * BN + b * BOX_COLS + sj * CPC + c;
-          if (lane < 8 && col < g.n_out && (int)blockIdx.x < num_tiles) {
-            atomicAdd(bn_sums + col, (double)s0);
-            atomicAdd(bn_sums + g.n_out + col, (double)s1);
-          }
+          const int lc = b * BOX_COLS + sj * CPC + c;
+          if (lane < 8) { red[(sw * BN + lc) * 2] = s0; red[(sw * BN + lc) * 2 + 1] = s1; }
+        }
+      }
+      named_barrier_sync(2, GATHER_THREADS);
+      for (int lc = st_t; lc < BN; lc += GATHER_THREADS) {
+        const int col = tn0 * BN + lc;
+        if (col < g.n_out && (int)blockIdx.x < num_tiles) {
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { s0 += (double)red[(w * BN + lc) * 2]; s1 += (double)red[(w * BN + lc) * 2 + 1]; }
+          atomicAdd(bn_sums + col, s0);
+          atomicAdd(bn_sums + g.n_out + col, s1);
         }
       }
     }
