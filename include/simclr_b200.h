@@ -194,6 +194,9 @@ SIMCLR_API int simclr_global_avgpool_bwd(const void* dy, int dy_dtype, void* dx,
 
 /* tcgen05 engine operands: K-major packed copies of the fp32 HWIO master.
  *   wf [Cout][Kp]       k = (r*S+s)*Cs + c,   Kp = round_up(R*S*Cs, 128B/elt)
+ *                       bf16 with Cs == 4 (the stem: 3 image channels + 1 zero):
+ *                       k = (r*(S+1) + s+1)*4 + c, Kp = round_up(R*(S+1)*4, 64); slot 0 of each
+ *                       filter row is zero, so a row is a whole number of 16-byte pixel pairs
  *   wd [Cin ][Kdp]      k = (r*S+s)*Cout + co, Kdp = round_up(R*S*Cout, 128B/elt)
  *                       (NULL: not needed, e.g. the stem) */
 SIMCLR_API int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, int64_t R,

@@ -36,7 +36,7 @@ for idx in sel:
     x = torch.randn(N, H, H, Cs, device='cuda').to(torch.bfloat16)
     dy = torch.randn(N, Ho, Ho, Cout, device='cuda').to(torch.bfloat16)
     w = torch.randn(k, k, Cin, Cout, device='cuda') * 0.05
-    K = k * k * Cs; Kp = (K + 63) // 64 * 64; Kd = (k * k * Cout + 63) // 64 * 64
+    K = k * (k + 1 if Cs == 4 else k) * Cs; Kp = (K + 63) // 64 * 64; Kd = (k * k * Cout + 63) // 64 * 64
     wf = torch.empty(Cout, Kp, dtype=torch.bfloat16, device='cuda')
     wd = torch.empty(Cin, Kd, dtype=torch.bfloat16, device='cuda') if Cs == Cin else None
     lib.pack_conv_weight(w, wf, wd, 1, k, k, Cin, Cs, Cout, Kp, st)

@@ -7,7 +7,8 @@
 namespace simclr {
 namespace {
 
-constexpr int BT = 256;
+constexpr int BT = 256;      // element-wise kernels
+constexpr int RT = 512;      // reduction kernels: one 512-thread CTA per SM
 
 template <typename T> __device__ __forceinline__ void load8(const T* p, float* f);
 template <> __device__ __forceinline__ void load8<float>(const float* p, float* f) {
@@ -41,13 +42,13 @@ template <> struct Raw8<__nv_bfloat16> {
 };
 
 // Thread layout shared by the reduction kernels: P threads span the
-// channel vectors of a row (power of two <= 256), 256/P "row lanes".
+// channel vectors of a row (power of two <= 512), 512/P "row lanes".
 struct RedLayout { int P, row_lanes, col_iters; };
 inline RedLayout red_layout(int64_t C) {
   const int cvecs = (int)(C / 8);
   int P = 1;
-  while (P * 2 <= cvecs && P * 2 <= BT) P *= 2;
-  RedLayout l; l.P = P; l.row_lanes = BT / P; l.col_iters = (cvecs + P - 1) / P;
+  while (P * 2 <= cvecs && P * 2 <= RT) P *= 2;
+  RedLayout l; l.P = P; l.row_lanes = RT / P; l.col_iters = (cvecs + P - 1) / P;
   return l;
 }
 
@@ -56,9 +57,9 @@ inline RedLayout red_layout(int64_t C) {
 // without residual: the mask [scale*y + shift > 0] is recomputed from y (a2 = scale,
 // zmask = shift, both fp32 [C]); dz is neither re-read from a mask tensor nor written.
 // The kernels are HBM-latency bound: each thread keeps 4 (modes 0, 2) or 2 (mode 1) rows of
-// 16-byte loads in flight, two 256-thread CTAs per SM.
+// 16-byte loads in flight, one 512-thread CTA per SM.
 template <typename T, typename Ty, int MODE>
-__global__ void __launch_bounds__(BT, 2)
+__global__ void __launch_bounds__(RT, 1)
 bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __restrict__ zmask_,
                  const Ty* __restrict__ y, int64_t rows, int C, int P, int rows_per_block,
                  const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ sums) {
@@ -66,7 +67,7 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
   const T* __restrict__ a2 = MODE == 2 ? nullptr : (const T*)a2_;
   const T* __restrict__ zmask = MODE == 2 ? nullptr : (const T*)zmask_;
   const int tx = threadIdx.x % P, ty = threadIdx.x / P;
-  const int row_lanes = BT / P;
+  const int row_lanes = RT / P;
   const int cvecs = C / 8;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
@@ -185,8 +186,8 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mine[i] = s0[i]; mine[8 + i] = s1[i]; }
     __syncthreads();
-    // P*16 values to reduce over row_lanes; thread t handles value index t, t+BT, ...
-    for (int idx = threadIdx.x; idx < P * 16; idx += BT) {
+    // P*16 values to reduce over row_lanes; thread t handles value index t, t+RT, ...
+    for (int idx = threadIdx.x; idx < P * 16; idx += RT) {
       const int px = idx / 16, e = idx % 16;
       const int c8 = (cv - tx + px);
       if (c8 >= cvecs) continue;
@@ -345,18 +346,17 @@ int launch_reduce(void* a, const void* a2, const void* zmask, const void* y, int
                   const float* mean, const float* rstd, double* sums, cudaStream_t st) {
   const RedLayout l = red_layout(C);
   int64_t nblocks = (rows + l.row_lanes * 8 - 1) / (l.row_lanes * 8);
-  // 2 CTAs of 256 threads are resident per SM (__launch_bounds__(BT, 2)): one wave of fat blocks.  Every block ends
-  // with one fp64 atomic per column, and same-address atomics serialise in L2 (~30 ns each): 8 waves of blocks
-  // cost ~30 us of atomic tail per launch, one wave a quarter of that.
-  const int64_t cap = (int64_t)num_sms() * 2;
+  // One 512-thread CTA per SM, a single wave.  Every block ends with one fp64 atomic per column, and same-address
+  // atomics serialise in L2 (~30 ns each): with 8 waves of 256-thread blocks the atomic tail was ~30 us per launch.
+  const int64_t cap = (int64_t)num_sms();
   if (nblocks > cap) nblocks = cap;
   if (nblocks < 1) nblocks = 1;
   const int rows_per_block = (int)((rows + nblocks - 1) / nblocks);
   nblocks = (rows + rows_per_block - 1) / rows_per_block;
-  const size_t smem = (size_t)BT * 16 * sizeof(float);
+  const size_t smem = (size_t)RT * 16 * sizeof(float);
   cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st);
   if (e != cudaSuccess) { set_error("bn reduce memset: %s", cudaGetErrorString(e)); return (int)e; }
-  bn_reduce_kernel<T, Ty, MODE><<<(unsigned)nblocks, BT, smem, st>>>(
+  bn_reduce_kernel<T, Ty, MODE><<<(unsigned)nblocks, RT, smem, st>>>(
       (T*)a, a2, zmask, (const Ty*)y, rows, (int)C, l.P, rows_per_block, mean, rstd, sums);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;

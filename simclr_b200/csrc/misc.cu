@@ -113,6 +113,8 @@ __global__ void add_inplace_kernel(T* __restrict__ a, const T* __restrict__ b, i
 
 // fp32 HWIO [R][S][Cin][Cout] -> wf [Cout][Kp] (k=(r*S+s)*Cs+c, zero padded) and
 // wd [Cin][Kdp] (k=(r*S+s)*Cout+co, zero padded to the K block).
+// bf16 with 4 stored channels (the stem): k = (r*(S+1) + s+1)*4 + c, slot s' = 0 of every filter
+// row zero -- S+1 slots make a filter row a whole number of 16-byte pixel pairs.
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int R,
                                    int S, int Cin, int Cs, int Cout, int Kp, int Kdp) {
@@ -123,7 +125,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
       const int co = (int)(i / Kp), k = (int)(i % Kp);
       const int tap = k / Cs, c = k % Cs;
       float v = 0.f;
-      if (tap < R * S && c < Cin) v = w[((int64_t)tap * Cin + c) * Cout + co];
+      if (sizeof(T) == 2 && Cs == 4) {
+        const int r = tap / (S + 1), sp = tap % (S + 1);
+        if (r < R && sp >= 1 && c < Cin) v = w[((int64_t)(r * S + sp - 1) * Cin + c) * Cout + co];
+      } else if (tap < R * S && c < Cin) {
+        v = w[((int64_t)tap * Cin + c) * Cout + co];
+      }
       wf[i] = from_f<T>(v);
     } else {
       const int64_t j = i - nf;
@@ -355,7 +362,9 @@ int simclr_add_inplace(void* a, const void* b, int dtype, int64_t n, void* strea
 int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, int64_t R, int64_t S, int64_t Cin,
                             int64_t Cs, int64_t Cout, int64_t Kp, void* stream) {
   SIMCLR_CHECK_ARG(w_hwio && wf, "pack_conv_weight: null pointer");
-  SIMCLR_CHECK_ARG(R > 0 && S > 0 && Cin > 0 && Cs >= Cin && Cout > 0 && Kp >= R * S * Cs, "pack_conv_weight: bad shape");
+  const int64_t Sk = (dtype == SIMCLR_BF16 && Cs == 4) ? S + 1 : S;      // bf16 stem: S+1 slots per filter row
+  SIMCLR_CHECK_ARG(R > 0 && S > 0 && Cin > 0 && Cs >= Cin && Cout > 0 && Kp >= R * Sk * Cs,
+                   "pack_conv_weight: bad shape (Kp=%lld < %lld)", (long long)Kp, (long long)(R * Sk * Cs));
   SIMCLR_CHECK_ARG(wd == nullptr || Cs == Cin, "pack_conv_weight: dgrad copy needs Cs == Cin");
   cudaStream_t st = (cudaStream_t)stream;
   const int kbe = dtype == SIMCLR_BF16 ? 64 : 32;

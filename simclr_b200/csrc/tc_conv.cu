@@ -35,7 +35,8 @@ struct Geom {
   void* out;
   int mode;            // 0: out pixel -> in pixel = p*stride - pad + r ; 1 (dgrad): (p + pad - r)/stride
   int H, W, C;         // dims of the gathered tensor
-  int R, S, RS, stride, pad_h, pad_w;
+  int R, S, RS, stride, stride_w, pad_h, pad_w;   // stride: rows (and columns unless stride_w differs: stem pixel pairs)
+  int s2;              // stem K order: S+1 slots of 4 channels per filter row (0: ordinary (r, s, c) order)
   FastDiv dPQ, dQ, dC, dS;
   long long M;         // GEMM rows (pixels)
   int n_out, ldc;      // valid output columns, output row stride (elements)
@@ -496,7 +497,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             g.dQ.divmod(rem, p, q);
             rpix[i] = (int)n * g.H * g.W;
             rbh[i] = g.mode == 0 ? (int)p * g.stride - g.pad_h : (int)p + g.pad_h;
-            rbw[i] = g.mode == 0 ? (int)q * g.stride - g.pad_w : (int)q + g.pad_w;
+            rbw[i] = g.mode == 0 ? (int)q * g.stride_w - g.pad_w : (int)q + g.pad_w;
           } else { rpix[i] = -1; rbh[i] = 0; rbw[i] = 0; }
         }
         const T* src = reinterpret_cast<const T*>(g.src);
@@ -641,8 +642,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         }
       } else {
         const int k = tk * 128 + warp * 32 + lane;           // row of the [R*S*Cs][Cout] matrix
-        uint32_t tap, c; g.dC.divmod((uint32_t)k, tap, c);
-        const bool row_ok = (int)tap < g.RS && (int)c < g.Cin;
+        uint32_t tap, c; bool row_ok;
+        if (g.s2) {          // stem K order: (r, s' in [0, S], c in [0, 4)); s' = 0 is the zero slot
+          const int t4 = k >> 2, r = t4 / g.s2, sp = t4 - r * g.s2;
+          c = (uint32_t)(k & 3);
+          row_ok = r < g.R && sp >= 1 && (int)c < g.Cin;
+          tap = (uint32_t)(r * (g.s2 - 1) + sp - 1);
+        } else {
+          g.dC.divmod((uint32_t)k, tap, c);
+          row_ok = (int)tap < g.RS && (int)c < g.Cin;
+        }
         float* drow = dw + ((long long)tap * g.Cin + c) * g.Cout;
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; ++cc) {
@@ -783,7 +792,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
           const uint32_t dst = a_addr + (q / PXS) * ATOM_BYTES + sw128_offset(px, j);
           const bool in_m = sm[e] < g.M;
           const int pix = sn[e] * g.H * g.W;
-          const int bh = sp[e] * g.stride - g.pad_h, bw = sq[e] * g.stride - g.pad_w;
+          const int bh = sp[e] * g.stride - g.pad_h, bw = sq[e] * g.stride_w - g.pad_w;
           if (!SMALLC) {
             const int h = bh + pdr[i], w = bw + pds[i];
             const bool ok = pk[i] && in_m && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W;
@@ -907,6 +916,22 @@ inline bool plan_im2col(int mode, int64_t Hs, int64_t Ws, int64_t Cs, int64_t P,
   return true;
 }
 
+// Geometry of the stem's K order (see run_igemm).
+struct StemGeom { bool pairs; int64_t S, W; int pad_w, stride_w; };
+inline StemGeom stem_geom(bool smallc, int mode, int64_t W, int64_t S, int64_t stride) {
+  StemGeom sg; sg.pairs = false; sg.S = S; sg.W = W; sg.pad_w = (int)((S - 1) / 2); sg.stride_w = (int)stride;
+  if (!smallc) return sg;
+  const int pad = (int)((S - 1) / 2);
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("SIMCLR_TC_STEM_PAIRS"); en = (e && e[0] == '0') ? 0 : 1; }
+  if (en && mode == 0 && stride == 2 && (pad & 1) && W % 2 == 0) {
+    sg.pairs = true; sg.S = (S + 1) / 2; sg.W = W / 2; sg.pad_w = (pad + 1) / 2; sg.stride_w = 1;
+  } else {
+    sg.S = S + 1; sg.pad_w = pad + 1;
+  }
+  return sg;
+}
+
 // Shared driver for fprop (mode 0) and dgrad (mode 1).
 //   gathered tensor [N][Hs][Ws][Cs]; GEMM rows = N*P*Q; weights wk [n_out][Kp]
 int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, int out_dtype, int64_t N, int64_t Hs,
@@ -914,19 +939,29 @@ int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, i
               cudaStream_t st, const char* what, double* bn_sums = nullptr) {
   const int es = dtype == SIMCLR_BF16 ? 2 : 4;
   const int KBE = 128 / es, CH = 16 / es;
-  const bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);
+  bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);
   if (!(Cs % CH == 0 || smallc)) { set_error("%s: stored channels (%lld) must be a multiple of %d", what, (long long)Cs, CH); return SIMCLR_ERR_UNSUPPORTED; }
+  if (smallc && mode != 0) { set_error("%s: 4-channel tensors are only supported as the conv input", what); return SIMCLR_ERR_UNSUPPORTED; }
   if (!aligned16(src) || !aligned16(wk)) { set_error("%s: operands must be 16-byte aligned", what); return SIMCLR_ERR_INVALID_ARG; }
   const int64_t M = N * P * Q;
   if (M >= (1ll << 31)) { set_error("%s: M too large", what); return SIMCLR_ERR_UNSUPPORTED; }
-  const int64_t K = R * S * Cs;
+  // Stem (4 stored channels, bf16): K runs over (r, s' in [0, S], c) with a zero slot s' = 0, i.e. the
+  // filter is S+1 wide with one more pixel of left padding.  With stride 2, odd padding and an even
+  // width the S+1 slots are whole 16-byte pixel pairs: the tensor is then read as [N][H][W/2][8] with
+  // (S+1)/2 taps per row, unit column stride, and goes through the ordinary 16-byte gather.
+  StemGeom sg = stem_geom(smallc, mode, Ws, S, stride);
+  if (sg.pairs) { smallc = false; Cs = 8; Ws = sg.W; }
+  const int64_t Sk = smallc || sg.pairs ? sg.S : S;
+  const int64_t K = R * Sk * Cs;
   const int64_t Kp = (K + KBE - 1) / KBE * KBE;
   const int bn = pick_bn(n_out);
   Geom g;
   g.src = src; g.out = out; g.mode = mode;
-  g.H = (int)Hs; g.W = (int)Ws; g.C = (int)Cs; g.R = (int)R; g.S = (int)S; g.RS = (int)(R * S);
+  g.H = (int)Hs; g.W = (int)Ws; g.C = (int)Cs; g.R = (int)R; g.S = (int)Sk; g.RS = (int)(R * Sk);
   g.stride = (int)stride; g.pad_h = (int)((R - 1) / 2); g.pad_w = (int)((S - 1) / 2);
-  g.dPQ = FastDiv((uint32_t)(P * Q)); g.dQ = FastDiv((uint32_t)Q); g.dC = FastDiv((uint32_t)Cs); g.dS = FastDiv((uint32_t)S);
+  g.stride_w = (int)stride; g.s2 = 0;
+  if (smallc || sg.pairs) { g.pad_w = sg.pad_w; g.stride_w = sg.stride_w; g.s2 = (int)S + 1; }
+  g.dPQ = FastDiv((uint32_t)(P * Q)); g.dQ = FastDiv((uint32_t)Q); g.dC = FastDiv((uint32_t)Cs); g.dS = FastDiv((uint32_t)Sk);
   g.P = (int)P; g.Q = (int)Q; g.adv_p = g.adv_q = 0;
   g.M = M; g.n_out = (int)n_out; g.ldc = (int)n_out; g.num_kb = (int)(Kp / KBE);
   g.tiles_m = (int)((M + 127) / 128); g.tiles_n = (int)((n_out + bn - 1) / bn);
@@ -1019,7 +1054,7 @@ int run_dgrad_strided(const void* dy, const void* wd, void* dx, int dtype, int o
       const int64_t M = N * P2 * Q2;
       g.src = dy; g.out = dx; g.mode = 0;
       g.H = (int)Ho; g.W = (int)Wo; g.C = (int)Cout; g.R = 1; g.S = 1; g.RS = nt;
-      g.stride = 1; g.pad_h = 0; g.pad_w = 0;
+      g.stride = 1; g.stride_w = 1; g.s2 = 0; g.pad_h = 0; g.pad_w = 0;
       g.dPQ = FastDiv((uint32_t)(P2 * Q2)); g.dQ = FastDiv((uint32_t)Q2); g.dC = FastDiv((uint32_t)Cout); g.dS = FastDiv(1);
       g.P = (int)P2; g.Q = (int)Q2; g.adv_p = g.adv_q = 0;
       g.M = M; g.n_out = (int)Cin; g.ldc = (int)Cin;
@@ -1138,7 +1173,7 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   }
   const int es = dtype == SIMCLR_BF16 ? 2 : 4;
   const int ATOM_E = 128 / es, CH = 16 / es;
-  const bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);
+  bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);
   if (!(Cs % CH == 0 || smallc)) { set_error("conv2d_wgrad_tc: stored channels (%lld) must be a multiple of %d", (long long)Cs, CH); return SIMCLR_ERR_UNSUPPORTED; }
   if ((Cout * es) % 16 != 0) { set_error("conv2d_wgrad_tc: Cout*elt must be a multiple of 16 bytes"); return SIMCLR_ERR_UNSUPPORTED; }
   SIMCLR_CHECK_ARG(aligned16(x) && aligned16(dy), "conv2d_wgrad_tc: operands must be 16-byte aligned");
@@ -1147,15 +1182,23 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   if (M >= (1ll << 31)) { set_error("conv2d_wgrad_tc: M too large"); return SIMCLR_ERR_UNSUPPORTED; }
   const int pxs = dtype == SIMCLR_BF16 ? 64 : 32;
   const int bn = pick_bn(Cout);
+  // the stem's K order and its pixel-pair reading (see run_igemm); dW keeps the [R][S][Cin][Cout] layout
+  const StemGeom sg = stem_geom(smallc, 0, W, S, stride);
+  const bool stem = smallc;
+  int64_t Wg = W;
+  if (sg.pairs) { smallc = false; Cs = 8; Wg = sg.W; }
+  const int64_t Sk = stem ? sg.S : S;
   Geom g;
   g.src = x; g.out = nullptr; g.mode = 0;
-  g.H = (int)H; g.W = (int)W; g.C = (int)Cs; g.R = (int)R; g.S = (int)S; g.RS = (int)(R * S);
+  g.H = (int)H; g.W = (int)Wg; g.C = (int)Cs; g.R = (int)R; g.S = (int)Sk; g.RS = (int)(R * Sk);
   g.stride = (int)stride; g.pad_h = (int)((R - 1) / 2); g.pad_w = (int)((S - 1) / 2);
-  g.dPQ = FastDiv((uint32_t)(Ho * Wo)); g.dQ = FastDiv((uint32_t)Wo); g.dC = FastDiv((uint32_t)Cs); g.dS = FastDiv((uint32_t)S);
+  g.stride_w = (int)stride; g.s2 = 0;
+  if (stem) { g.pad_w = sg.pad_w; g.stride_w = sg.stride_w; g.s2 = (int)S + 1; }
+  g.dPQ = FastDiv((uint32_t)(Ho * Wo)); g.dQ = FastDiv((uint32_t)Wo); g.dC = FastDiv((uint32_t)Cs); g.dS = FastDiv((uint32_t)Sk);
   g.P = (int)Ho; g.Q = (int)Wo; g.adv_p = pxs / (int)Wo; g.adv_q = pxs % (int)Wo;
   g.M = M; g.n_out = (int)Cout; g.ldc = (int)Cout;
   g.num_kb = (int)((M + pxs - 1) / pxs);
-  g.tiles_m = (int)((R * S * Cs + 127) / 128); g.tiles_n = (int)((Cout + bn - 1) / bn);
+  g.tiles_m = (int)((R * Sk * Cs + 127) / 128); g.tiles_n = (int)((Cout + bn - 1) / bn);
   g.Cin = (int)Cin; g.Cout = (int)Cout;
   g.use_tab = 0; g.cblocks = 1; g.os = 0; g.oh0 = g.ow0 = 0; g.OH = g.OW = 0; g.tap_sign = 1;
   const int tiles = g.tiles_m * g.tiles_n;
@@ -1182,7 +1225,7 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   }
   // splits are combined by TMA reduce-add when dW is a plain [R*S*Cin][Cout] fp32 matrix with 16-byte rows
   CUtensorMap tdw;
-  const bool tma_red = !smallc && Cs == Cin && aligned16(dw) && (Cout * 4) % 16 == 0;
+  const bool tma_red = !stem && Cs == Cin && aligned16(dw) && (Cout * 4) % 16 == 0;
   if (tma_red) { rc = make_tmap_2d(&tdw, dw, 4, (uint64_t)(R * S * Cin), (uint64_t)Cout, (uint64_t)Cout * 4, 128, 32); if (rc) return rc; }
   else tdw = tdy;
   SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(R * S * Cin * Cout) * sizeof(float), st));

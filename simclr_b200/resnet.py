@@ -121,7 +121,8 @@ class ConvOp:
     def _pack(self, e):
         es = 2 if e.act_dtype == torch.bfloat16 else 4
         kbe = 128 // es
-        K = self.R * self.S * self.cs
+        # the bf16 stem (4 stored channels) packs S+1 slots per filter row (simclr_b200.h, pack_conv_weight)
+        K = self.R * (self.S + 1 if (self.cs == 4 and es == 2) else self.S) * self.cs
         Kp = (K + kbe - 1) // kbe * kbe
         if self.wf is None or self.wf.dtype != e.act_dtype:
             self.wf = e.empty((self.cout, Kp))

@@ -32,6 +32,9 @@ CASES = [
     (3, 9, 9, 64, 64, 64, 3, 2),         # odd extent, strided: im2col fprop/wgrad, dgrad classes of unequal size
     (2, 12, 12, 64, 64, 128, 3, 2),      # 64-channel strided 3x3 (two taps per 128 k-rows in wgrad)
     (1, 9, 11, 64, 64, 64, 5, 1),        # 5x5, rectangular image
+    (2, 31, 31, 3, 4, 64, 7, 2),         # stem on an odd width: 8-byte gather (no pixel pairs)
+    (2, 16, 16, 3, 4, 64, 3, 1),         # CIFAR stem: 3x3 stride 1 on 4 stored channels
+    (3, 20, 28, 3, 4, 64, 7, 2),         # stem, rectangular, pixel-pair path, ragged last tile
 ]
 
 
@@ -48,7 +51,7 @@ def _pack(w, dtype, k, Cin, Cs, Cout, want_wd=True):
     from simclr_b200._lib import lib, stream_ptr, DTYPE_CODE
     es = 2 if dtype == torch.bfloat16 else 4
     kbe = 128 // es
-    K = k * k * Cs
+    K = k * (k + 1 if (Cs == 4 and es == 2) else k) * Cs     # bf16 stem: S+1 slots per filter row
     Kp = (K + kbe - 1) // kbe * kbe
     wf = torch.empty(Cout, Kp, dtype=dtype, device='cuda')
     kd = k * k * Cout
