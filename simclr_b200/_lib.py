@@ -13,7 +13,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(HERE, '..', 'include', 'simclr_b200.h')
-LIB_PATH = os.path.join(HERE, 'libsimclr_b200.so')
+LIB_PATH = os.environ.get('SIMCLR_B200_LIB') or os.path.join(HERE, 'libsimclr_b200.so')   # override: A/B builds
 
 F32, BF16 = 0, 1
 DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16}

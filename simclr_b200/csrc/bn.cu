@@ -7,8 +7,7 @@
 namespace simclr {
 namespace {
 
-constexpr int BT = 256;      // element-wise kernels
-constexpr int RT = 512;      // reduction kernels: one 512-thread CTA per SM
+constexpr int BT = 256;
 
 template <typename T> __device__ __forceinline__ void load8(const T* p, float* f);
 template <> __device__ __forceinline__ void load8<float>(const float* p, float* f) {
@@ -42,13 +41,13 @@ template <> struct Raw8<__nv_bfloat16> {
 };
 
 // Thread layout shared by the reduction kernels: P threads span the
-// channel vectors of a row (power of two <= 512), 512/P "row lanes".
+// channel vectors of a row (power of two <= 256), 256/P "row lanes".
 struct RedLayout { int P, row_lanes, col_iters; };
 inline RedLayout red_layout(int64_t C) {
   const int cvecs = (int)(C / 8);
   int P = 1;
-  while (P * 2 <= cvecs && P * 2 <= RT) P *= 2;
-  RedLayout l; l.P = P; l.row_lanes = RT / P; l.col_iters = (cvecs + P - 1) / P;
+  while (P * 2 <= cvecs && P * 2 <= BT) P *= 2;
+  RedLayout l; l.P = P; l.row_lanes = BT / P; l.col_iters = (cvecs + P - 1) / P;
   return l;
 }
 
@@ -57,33 +56,46 @@ inline RedLayout red_layout(int64_t C) {
 // without residual: the mask [scale*y + shift > 0] is recomputed from y (a2 = scale,
 // zmask = shift, both fp32 [C]); dz is neither re-read from a mask tensor nor written.
 // The kernels are HBM-latency bound: each thread keeps 4 (modes 0, 2) or 2 (mode 1) rows of
-// 16-byte loads in flight, one 512-thread CTA per SM.
+// 16-byte loads in flight, two 256-thread CTAs per SM.
 template <typename T, typename Ty, int MODE>
-__global__ void __launch_bounds__(RT, 1)
+__global__ void __launch_bounds__(BT, 2)
 bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __restrict__ zmask_,
                  const Ty* __restrict__ y, int64_t rows, int C, int P, int rows_per_block,
                  const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ sums) {
-  extern __shared__ float sh[];   // [row_lanes][P*8][2]
+  extern __shared__ double sh[];  // [row_lanes][P*8][2]
   const T* __restrict__ a2 = MODE == 2 ? nullptr : (const T*)a2_;
   const T* __restrict__ zmask = MODE == 2 ? nullptr : (const T*)zmask_;
   const int tx = threadIdx.x % P, ty = threadIdx.x / P;
-  const int row_lanes = RT / P;
+  const int row_lanes = BT / P;
   const int cvecs = C / 8;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
   const int64_t lane_step = (int64_t)row_lanes * C;
   for (int cv = tx; cv < cvecs + (P - 1 - ((cvecs - 1) % P)); cv += P) {   // uniform trip count across tx
     const bool active = cv < cvecs;
+    // fp32 sums over the 2-4 rows in flight, folded into fp64 running sums after every group: the column
+    // sums of a BatchNorm backward cancel heavily (they vanish analytically below another BatchNorm), so
+    // long fp32 accumulations would leave their value to rounding noise.
     float s0[8], s1[8];
+    double d0[8], d1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = 0.f; }
+    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = 0.f; d0[i] = d1[i] = 0.0; }
+    auto fold = [&]() {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { d0[i] += (double)s0[i]; d1[i] += (double)s1[i]; s0[i] = 0.f; s1[i] = 0.f; }
+    };
     if (active) {
       int64_t r = r0 + ty;
       if (MODE == 0) {
+        // Shifted sums: u = x - pivot with pivot = row 0 of the tensor (any sample of the channel).  The
+        // fp32 squares are then O(variance) instead of O(mean^2), so var = E[x^2] - mean^2 keeps its digits
+        // for nearly constant channels (|mean| >> sigma); the shift is undone in fp64 by the block tree.
+        float pv[8];
+        { Raw8<T> q0; q0.ld(a + (int64_t)cv * 8); q0.to(pv); }
         auto acc = [&](const Raw8<T>& q) {
           float v[8]; q.to(v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { s0[i] += v[i]; s1[i] = fmaf(v[i], v[i], s1[i]); }
+          for (int i = 0; i < 8; ++i) { const float u = v[i] - pv[i]; s0[i] += u; s1[i] = fmaf(u, u, s1[i]); }
         };
         for (; r + 3 * row_lanes < r1; r += 4 * row_lanes) {
           const T* p = a + r * C + (int64_t)cv * 8;
@@ -92,8 +104,10 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           for (int u = 0; u < 4; ++u) q[u].ld(p + u * lane_step);
 #pragma unroll
           for (int u = 0; u < 4; ++u) acc(q[u]);
+          fold();
         }
         for (; r < r1; r += row_lanes) { Raw8<T> q; q.ld(a + r * C + (int64_t)cv * 8); acc(q); }
+        fold();
       } else if (MODE == 2) {
         float mu[8], msc[8], msh[8];
 #pragma unroll
@@ -119,13 +133,15 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           for (int u = 0; u < 4; ++u) { qg[u].ld(a + off + u * lane_step); qy[u].ld(y + off + u * lane_step); }
 #pragma unroll
           for (int u = 0; u < 4; ++u) acc(qg[u], qy[u]);
+          fold();
         }
         for (; r < r1; r += row_lanes) {
           const int64_t off = r * C + (int64_t)cv * 8;
           Raw8<T> qg; Raw8<Ty> qy; qg.ld(a + off); qy.ld(y + off); acc(qg, qy);
         }
+        fold();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s1[i] *= rstd[cv * 8 + i];
+        for (int i = 0; i < 8; ++i) d1[i] *= (double)rstd[cv * 8 + i];
       } else {
         float mu[8];
 #pragma unroll
@@ -166,6 +182,7 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u) acc(off + u * lane_step, qv[u], qw[u], qz[u], qy[u]);
+          fold();
         }
         for (; r < r1; r += row_lanes) {
           const int64_t off = r * C + (int64_t)cv * 8;
@@ -176,24 +193,36 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           qy.ld(y + off);
           acc(off, qv, qw, qz, qy);
         }
+        fold();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s1[i] *= rstd[cv * 8 + i];
+        for (int i = 0; i < 8; ++i) d1[i] *= (double)rstd[cv * 8 + i];
       }
     }
     // block tree over row lanes
     __syncthreads();
-    float* mine = sh + ((size_t)ty * P + tx) * 16;
+    double* mine = sh + ((size_t)ty * P + tx) * 16;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { mine[i] = s0[i]; mine[8 + i] = s1[i]; }
+    for (int i = 0; i < 8; ++i) { mine[i] = d0[i]; mine[8 + i] = d1[i]; }
     __syncthreads();
-    // P*16 values to reduce over row_lanes; thread t handles value index t, t+RT, ...
-    for (int idx = threadIdx.x; idx < P * 16; idx += RT) {
+    // P*16 values to reduce over row_lanes; thread t handles value index t, t+BT, ...
+    for (int idx = threadIdx.x; idx < P * 16; idx += BT) {
       const int px = idx / 16, e = idx % 16;
       const int c8 = (cv - tx + px);
       if (c8 >= cvecs) continue;
       double acc = 0.0;
-      for (int l = 0; l < row_lanes; ++l) acc += (double)sh[((size_t)l * P + px) * 16 + e];
+      for (int l = 0; l < row_lanes; ++l) acc += sh[((size_t)l * P + px) * 16 + e];
       const int ch = c8 * 8 + (e & 7);
+      if (MODE == 0) {         // undo the pivot shift: sum x = S0 + n p,  sum x^2 = S1 + 2 p S0 + n p^2
+        const double pvt = (double)to_f<T>(a[ch]);
+        const double n = (double)(r1 - r0);
+        if (e < 8) {
+          acc += n * pvt;
+        } else {
+          double a0 = 0.0;
+          for (int l = 0; l < row_lanes; ++l) a0 += sh[((size_t)l * P + px) * 16 + e - 8];
+          acc += 2.0 * pvt * a0 + n * pvt * pvt;
+        }
+      }
       atomicAdd(&sums[(e >> 3) * C + ch], acc);
     }
   }
@@ -346,17 +375,18 @@ int launch_reduce(void* a, const void* a2, const void* zmask, const void* y, int
                   const float* mean, const float* rstd, double* sums, cudaStream_t st) {
   const RedLayout l = red_layout(C);
   int64_t nblocks = (rows + l.row_lanes * 8 - 1) / (l.row_lanes * 8);
-  // One 512-thread CTA per SM, a single wave.  Every block ends with one fp64 atomic per column, and same-address
-  // atomics serialise in L2 (~30 ns each): with 8 waves of 256-thread blocks the atomic tail was ~30 us per launch.
-  const int64_t cap = (int64_t)num_sms();
+  // 2 CTAs of 256 threads are resident per SM (__launch_bounds__(BT, 2)): one wave of fat blocks.  Every block ends
+  // with one fp64 atomic per column, and same-address atomics serialise in L2 (~30 ns each): 8 waves of blocks
+  // cost ~30 us of atomic tail per launch, one wave a quarter of that.
+  const int64_t cap = (int64_t)num_sms() * 2;
   if (nblocks > cap) nblocks = cap;
   if (nblocks < 1) nblocks = 1;
   const int rows_per_block = (int)((rows + nblocks - 1) / nblocks);
   nblocks = (rows + rows_per_block - 1) / rows_per_block;
-  const size_t smem = (size_t)RT * 16 * sizeof(float);
+  const size_t smem = (size_t)BT * 16 * sizeof(double);
   cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st);
   if (e != cudaSuccess) { set_error("bn reduce memset: %s", cudaGetErrorString(e)); return (int)e; }
-  bn_reduce_kernel<T, Ty, MODE><<<(unsigned)nblocks, RT, smem, st>>>(
+  bn_reduce_kernel<T, Ty, MODE><<<(unsigned)nblocks, BT, smem, st>>>(
       (T*)a, a2, zmask, (const Ty*)y, rows, (int)C, l.P, rows_per_block, mean, rstd, sums);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
