@@ -8,7 +8,7 @@ st = _lib.stream_ptr()
 def mk(path):
     l = _lib._Lib(); keep = _lib.LIB_PATH; _lib.LIB_PATH = path; l.load(); _lib.LIB_PATH = keep; return l
 libs = {'main': mk(os.path.join(ROOT, 'simclr_b200', 'libsimclr_b200.so'))}
-for n in ('bnold', 'bn_f0'):
+for n in ():   # side builds for A/B runs go here
     p = os.path.join(ROOT, 'build_tmp', 'libsimclr_%s.so' % n)
     if os.path.exists(p): libs[n] = mk(p)
 torch.manual_seed(0)
