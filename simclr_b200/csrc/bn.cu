@@ -73,7 +73,7 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
   const int64_t lane_step = (int64_t)row_lanes * C;
   for (int cv = tx; cv < cvecs + (P - 1 - ((cvecs - 1) % P)); cv += P) {   // uniform trip count across tx
     const bool active = cv < cvecs;
-    // fp32 sums over the 2-4 rows in flight, folded into fp64 running sums after every group: the column
+    // fp32 sums over a few groups of the 2-4 rows in flight, folded into fp64 running sums: the column
     // sums of a BatchNorm backward cancel heavily (they vanish analytically below another BatchNorm), so
     // long fp32 accumulations would leave their value to rounding noise.
     float s0[8], s1[8];
@@ -84,6 +84,8 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
 #pragma unroll
       for (int i = 0; i < 8; ++i) { d0[i] += (double)s0[i]; d1[i] += (double)s1[i]; s0[i] = 0.f; s1[i] = 0.f; }
     };
+    int groups = 0;
+    auto fold_some = [&]() { if ((++groups & 3) == 0) fold(); };   // every 4th group: fp32->fp64 converts are slow
     if (active) {
       int64_t r = r0 + ty;
       if (MODE == 0) {
@@ -104,7 +106,7 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           for (int u = 0; u < 4; ++u) q[u].ld(p + u * lane_step);
 #pragma unroll
           for (int u = 0; u < 4; ++u) acc(q[u]);
-          fold();
+          fold_some();
         }
         for (; r < r1; r += row_lanes) { Raw8<T> q; q.ld(a + r * C + (int64_t)cv * 8); acc(q); }
         fold();
@@ -133,7 +135,7 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           for (int u = 0; u < 4; ++u) { qg[u].ld(a + off + u * lane_step); qy[u].ld(y + off + u * lane_step); }
 #pragma unroll
           for (int u = 0; u < 4; ++u) acc(qg[u], qy[u]);
-          fold();
+          fold_some();
         }
         for (; r < r1; r += row_lanes) {
           const int64_t off = r * C + (int64_t)cv * 8;
@@ -182,7 +184,7 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u) acc(off + u * lane_step, qv[u], qw[u], qz[u], qy[u]);
-          fold();
+          fold_some();
         }
         for (; r < r1; r += row_lanes) {
           const int64_t off = r * C + (int64_t)cv * 8;
