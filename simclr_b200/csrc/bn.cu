@@ -73,9 +73,9 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
   const int64_t lane_step = (int64_t)row_lanes * C;
   for (int cv = tx; cv < cvecs + (P - 1 - ((cvecs - 1) % P)); cv += P) {   // uniform trip count across tx
     const bool active = cv < cvecs;
-    // fp32 sums over a few groups of the 2-4 rows in flight, folded into fp64 running sums: the column
-    // sums of a BatchNorm backward cancel heavily (they vanish analytically below another BatchNorm), so
-    // long fp32 accumulations would leave their value to rounding noise.
+    // Per-thread sums are fp32 (a few hundred rows at most), everything from the block tree on is fp64.  The
+    // forward statistics (mode 0) additionally fold into fp64 every few groups; doing that in the backward
+    // modes costs ~13% of their bandwidth (fp32->fp64 converts are slow) for no measurable accuracy.
     float s0[8], s1[8];
     double d0[8], d1[8];
 #pragma unroll
@@ -135,7 +135,6 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           for (int u = 0; u < 4; ++u) { qg[u].ld(a + off + u * lane_step); qy[u].ld(y + off + u * lane_step); }
 #pragma unroll
           for (int u = 0; u < 4; ++u) acc(qg[u], qy[u]);
-          fold_some();
         }
         for (; r < r1; r += row_lanes) {
           const int64_t off = r * C + (int64_t)cv * 8;
@@ -184,7 +183,6 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u) acc(off + u * lane_step, qv[u], qw[u], qz[u], qy[u]);
-          fold_some();
         }
         for (; r < r1; r += row_lanes) {
           const int64_t off = r * C + (int64_t)cv * 8;
