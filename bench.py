@@ -139,7 +139,7 @@ def run_reference(args):
     sec, loss = oracle_step_time(args, args.cpu_batch, max(1, args.steps), max(1, min(args.warmup, 1)))
     ips = args.cpu_batch / sec
     line = {
-        'impl': 'reference', 'metric': 'images/sec pretrain step', 'value': ips, 'unit': 'images/s', 'n_gpus': 0,
+        'impl': 'reference', 'metric': 'images/sec pretrain step', 'value': ips, 'unit': 'images/s', 'n_gpus': max(1, args.gpus),
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload, 'sample': 'batch %d per step (CPU throughput is ~batch independent)' % args.cpu_batch},
@@ -149,7 +149,7 @@ def run_reference(args):
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'loss': loss,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -350,7 +350,7 @@ def run_b200(args):
             'clocks': sampler.summary() if sampler else None,
             'roofline': roof, 'cpu_baseline': cpu, 'loss': loss_val,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist.is_initialized():
         dist.destroy_process_group()
 
@@ -366,8 +366,28 @@ def _watchdog(seconds):
     signal.alarm(seconds)
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there when
+    NCCL_DEBUG is set) write to fd 1 directly, so fd 1 is pointed at stderr for the whole run and the
+    saved descriptor is used for the result line only."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
     args = parse_args()
+    _quiet_stdout()
     _watchdog(int(os.environ.get('SIMCLR_BENCH_TIMEOUT', '900')))
     if args.impl == 'reference':
         run_reference(args)
