@@ -18,7 +18,12 @@ namespace {
 constexpr int A_STAGE_BYTES = 128 * 128;     // 128 rows x 128 B
 constexpr int PIPE_BYTES = 192 * 1024;
 constexpr int EPI_THREADS = 128;
-constexpr int GATHER_THREADS = 128;
+constexpr int GATHER_THREADS = 256;   // 8 gather warps: two per scheduler hide each other's address arithmetic
+constexpr int STATS_THREADS = 128;    // 4 statistics warps (TMA-fed fprop)
+constexpr int GROWS = GATHER_THREADS / 8;   // tile rows covered by one pass of the gather threads (8 threads per row)
+constexpr int GPT = 128 / GROWS;            // 16-byte pieces per gather thread per stage
+constexpr int igemm_threads(bool a_tma, bool stats) { return a_tma ? (stats ? 192 + STATS_THREADS : 192) : 192 + GATHER_THREADS; }
+constexpr int wgrad_threads(bool a_tma) { return a_tma ? 192 : 192 + GATHER_THREADS; }
 
 template <int BN> struct Tile {
   static constexpr int B_STAGE_BYTES = BN * 128;
@@ -144,7 +149,7 @@ __device__ __forceinline__ SmemCtl carve(uint8_t* base, int stage_bytes) {
 // fprop / dgrad / dense:  out[M][n_out] = gather(src)[M][K] * Wk[n_out][K]^T
 // ===========================================================================
 template <typename T, typename To, int BN, bool A_TMA, bool SMALLC, bool TMA_EPI, bool STATS>
-__global__ void __launch_bounds__((A_TMA && !STATS) ? 192 : 320, 1)
+__global__ void __launch_bounds__(igemm_threads(A_TMA, STATS), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_out, const Geom g, double* __restrict__ bn_sums) {
   using TL = Tile<BN>;
@@ -165,7 +170,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       mbar_init(&ctl.empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(&ctl.tmem_full[a], 1); mbar_init(&ctl.tmem_empty[a], EPI_THREADS / 32); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.sfull[a], 1); mbar_init(&ctl.sfree[a], GATHER_THREADS / 32); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl.sfull[a], 1); mbar_init(&ctl.sfree[a], STATS_THREADS / 32); }
     fence_barrier_init();
   }
   if (warp == 5 && lane == 0) {
@@ -463,8 +468,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           if (lane < 8) { red[(sw * BN + lc) * 2] = s0; red[(sw * BN + lc) * 2 + 1] = s1; }
         }
       }
-      named_barrier_sync(2, GATHER_THREADS);
-      for (int lc = st_t; lc < BN; lc += GATHER_THREADS) {
+      named_barrier_sync(2, STATS_THREADS);
+      for (int lc = st_t; lc < BN; lc += STATS_THREADS) {
         const int col = tn0 * BN + lc;
         if (col < g.n_out && (int)blockIdx.x < num_tiles) {
           double s0 = 0.0, s1 = 0.0;
@@ -482,15 +487,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       constexpr int D = TL::GATHER_DEPTH;
       const int gt = threadIdx.x - 192;
       const int j = gt & 7;              // 16-byte chunk within the 128-byte K block
-      const int row0 = gt >> 3;          // rows row0 + 16*i
+      const int row0 = gt >> 3;          // rows row0 + GROWS*i
       Pipe pi{0, 0}, pa{0, 0};
       int inflight = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / g.tiles_n;
-        int rpix[8], rbh[8], rbw[8];     // rpix: n*H*W of the gathered tensor (-1: row beyond M)
+        int rpix[GPT], rbh[GPT], rbw[GPT];     // rpix: n*H*W of the gathered tensor (-1: row beyond M)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long m = (long long)tm * 128 + row0 + 16 * i;
+        for (int i = 0; i < GPT; ++i) {
+          const long long m = (long long)tm * 128 + row0 + GROWS * i;
           if (m < g.M) {
             uint32_t n, rem, p, q;
             g.dPQ.divmod((uint32_t)m, n, rem);
@@ -509,18 +514,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             uint32_t tap, c; g.dC.divmod(k0, tap, c);
             const TapRef t = decode_tap(g, tap);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < GPT; ++i) {
               const int h = rbh[i] + t.dr, w = rbw[i] + t.ds;
               const bool ok = t.ok && rpix[i] >= 0 && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W;
               const T* p = src + (long long)(rpix[i] + h * g.W + w) * g.C + c;
-              cp_async16(a_addr + sw128_offset(row0 + 16 * i, j), ok ? (const void*)p : (const void*)src, ok ? 16u : 0u);
+              cp_async16(a_addr + sw128_offset(row0 + GROWS * i, j), ok ? (const void*)p : (const void*)src, ok ? 16u : 0u);
             }
           } else {
             // stem: 4 stored channels, so a 16-byte chunk covers two taps (8 bytes each)
             const TapRef t0 = decode_tap(g, k0 >> 2), t1 = decode_tap(g, (k0 >> 2) + 1);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t dst = a_addr + sw128_offset(row0 + 16 * i, j);
+            for (int i = 0; i < GPT; ++i) {
+              const uint32_t dst = a_addr + sw128_offset(row0 + GROWS * i, j);
               const int h0 = rbh[i] + t0.dr, w0 = rbw[i] + t0.ds, h1 = rbh[i] + t1.dr, w1 = rbw[i] + t1.ds;
               const bool ok0 = t0.ok && rpix[i] >= 0 && (unsigned)h0 < (unsigned)g.H && (unsigned)w0 < (unsigned)g.W;
               const bool ok1 = t1.ok && rpix[i] >= 0 && (unsigned)h1 < (unsigned)g.H && (unsigned)w1 < (unsigned)g.W;
@@ -558,7 +563,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 // Work item = (128 k-rows) x (BN couts) x (pixel split); fp32 atomics combine splits.
 // ===========================================================================
 template <typename T, int BN, bool SMALLC, bool A_TMA, bool TMA_RED>
-__global__ void __launch_bounds__(A_TMA ? 192 : 320, 1)
+__global__ void __launch_bounds__(wgrad_threads(A_TMA), 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
              const __grid_constant__ CUtensorMap tmap_dw, const Geom g, float* __restrict__ dw) {
   using TL = Tile<BN>;
@@ -748,12 +753,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     int inflight = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int tk, tn, kb0, kb1; decode(item, tk, tn, kb0, kb1);
-      // piece i of this thread: q = gt/8 + 16*i -> atom q / PXS, pixel q % PXS; its (tap, c) is fixed per item
-      int pdr[8], pds[8], pc[8]; bool pk[8];
-      int pdr2[8], pds2[8]; bool pk2[8];
+      // piece i of this thread: q = gt/8 + GROWS*i -> atom q / PXS, pixel q % PXS; its (tap, c) is fixed per item
+      int pdr[GPT], pds[GPT], pc[GPT]; bool pk[GPT];
+      int pdr2[GPT], pds2[GPT]; bool pk2[GPT];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int q = (gt >> 3) + 16 * i;
+      for (int i = 0; i < GPT; ++i) {
+        const int q = (gt >> 3) + GROWS * i;
         const int atom = q / PXS;
         const uint32_t k = (uint32_t)(tk * 128 + atom * ATOM_E + j * CH);
         if (!SMALLC) {
@@ -768,14 +773,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         }
       }
       const T* src = reinterpret_cast<const T*>(g.src);
-      // The thread's 8 pieces touch only NPX distinct pixels (piece i -> pixel slot i % NPX, atom i / NPX).
+      // The thread's GPT pieces touch only NPX distinct pixels (piece i -> pixel slot i % NPX, atom i / NPX).
       // Their (n, p, q) coordinates are decoded once per item and then walked forward by PXS per K block.
-      constexpr int NPX = PXS / 16;
+      constexpr int NPX = PXS / GROWS;
+      static_assert(NPX >= 1, "gather rows per pass must not exceed the pixels per stage");
       int sn[NPX], sp[NPX], sq[NPX];
       long long sm[NPX];
 #pragma unroll
       for (int e = 0; e < NPX; ++e) {
-        sm[e] = (long long)kb0 * PXS + (gt >> 3) + 16 * e;
+        sm[e] = (long long)kb0 * PXS + (gt >> 3) + GROWS * e;
         uint32_t nn, rem, p, qq;
         g.dPQ.divmod((uint32_t)min(sm[e], (long long)0x7fffffff), nn, rem);
         g.dQ.divmod(rem, p, qq);
@@ -785,9 +791,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         mbar_wait(&ctl.empty[pi.stage], pi.phase ^ 1, 80);
         const uint32_t a_addr = smem_u32(smem + (size_t)pi.stage * TL::STAGE_BYTES);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < GPT; ++i) {
           const int e = i % NPX;
-          const int q = (gt >> 3) + 16 * i;
+          const int q = (gt >> 3) + GROWS * i;
           const int px = q % PXS;
           const uint32_t dst = a_addr + (q / PXS) * ATOM_BYTES + sw128_offset(px, j);
           const bool in_m = sm[e] < g.M;
@@ -858,7 +864,7 @@ int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
     grid = grid / g.tiles_n * g.tiles_n;
     if (grid < g.tiles_n) grid = g.tiles_n;
   }
-  kern<<<grid, (A_TMA && !STATS) ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(ta, tb, tout, g, bn_sums);
+  kern<<<grid, igemm_threads(A_TMA, STATS), Tile<BN>::SMEM_BYTES, st>>>(ta, tb, tout, g, bn_sums);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
@@ -1095,7 +1101,7 @@ int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, const CUtensorMa
   static bool attr = false;
   if (!attr) { int rc = set_smem_attr(kern, Tile<BN>::SMEM_BYTES); if (rc) return rc; attr = true; }
   int grid = g.tiles_m * g.tiles_n * g.splits; if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, A_TMA ? 192 : 320, Tile<BN>::SMEM_BYTES, st>>>(tx, tdy, tdw, g, dw);
+  kern<<<grid, wgrad_threads(A_TMA), Tile<BN>::SMEM_BYTES, st>>>(tx, tdy, tdw, g, dw);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
