@@ -176,3 +176,43 @@ def test_augmentation_draws_follow_the_reference_ranges():
         assert -0.2 <= c['hue'] <= 0.2
         n_flip += d['flip']; n_jit += c['apply_jitter']; n_gray += c['apply_gray']
     assert 150 < n_flip < 250 and 280 < n_jit < 360 and 40 < n_gray < 120
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py contract (CPU arm): exactly one JSON line on stdout, with the reference-arm keys, even when a
+    library writes to fd 1 behind Python's back."""
+    import json, subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                        '--cpu_batch', '2', '--image_size', '32', '--resnet_depth', '18'],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS='4'))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'images/sec pretrain step' and d['unit'] == 'images/s'
+    assert d['higher_is_better'] is True and d['value'] > 0
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert 'workload' in d['config'] and 'model' not in d['config']
+
+
+def test_profiles_are_consistent_with_their_sources(tmp_path):
+    """profiles/: the committed launch list regenerates the committed share table and traffic.json, and the
+    traffic bench.py reports is within 10 % of the algorithmic bytes (no wasted DRAM re-reads)."""
+    import json, subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out_txt, out_json = tmp_path / 'shares.txt', tmp_path / 'traffic.json'
+    r = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'summarize_launches.py'),
+                        os.path.join(root, 'profiles', 'r01_launches_step.csv'), str(out_txt), str(out_json)],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    new = json.load(open(out_json)); old = json.load(open(os.path.join(root, 'profiles', 'traffic.json')))
+    assert new['launches'] == old['launches'] and abs(new['dram_bytes_per_launch'] - old['dram_bytes_per_launch']) < 1.0
+    assert open(out_txt).read() == open(os.path.join(root, 'profiles', 'r01_launch_shares.txt')).read()
+    latest = sorted(f for f in os.listdir(os.path.join(root, 'profiles')) if f.startswith('r01_bench_n1_v'))
+    latest.sort(key=lambda f: int(f.split('_v')[1].split('.')[0]))
+    line = json.load(open(os.path.join(root, 'profiles', latest[-1])))
+    roof = line['roofline']
+    assert roof['traffic'] is not None and 0.9 < roof['traffic'] / roof['algorithmic_bytes'] < 1.1
+    assert line['gpu_launches'] > 0 and line['e2e']['h2d_bytes_per_step'] > 0
