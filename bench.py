@@ -184,10 +184,12 @@ def run_b200(args):
 
     log('model built')
     # ---- capture -------------------------------------------------------------
-    # One CUDA graph per step on a single GPU.  With more than one rank the step is launched eagerly
-    # (NCCL collectives between the kernels): the ~700 launches per step cost a few ms of host time
-    # that hide behind a ~100 ms GPU step.
-    use_graph = (not args.no_graph) and world == 1
+    # One CUDA graph per step on a single GPU.  With more than one rank the in-step collectives (SyncBN
+    # statistics, embedding / lse all-gathers) are our own NVLink peer-memory kernels, so forward + backward
+    # is one graph, the NCCL gradient all-reduce sits between it and a second graph with the LARS update.
+    # Without peer memory (SIMCLR_COMM=nccl) the step is launched eagerly.
+    peer = trainer.strategy.comm is not None
+    use_graph = (not args.no_graph) and (world == 1 or peer)
     launches0 = lib.launch_count
     if use_graph:
         trainer.capture(features, labels, warmup=1)
@@ -344,7 +346,8 @@ def run_b200(args):
             'data': 'synthetic',
             'config': {'workload': workload_string(args, world),
                        'l2': 'inputs larger than L2 (activations are GBs per step)',
-                       'cuda_graph': use_graph, 'parallelism': 'dp%d' % world},
+                       'cuda_graph': use_graph, 'parallelism': 'dp%d' % world,
+                       'collectives': ('none' if world == 1 else ('nvlink peer-memory kernels (SyncBN, all-gathers) + NCCL gradient all-reduce' if peer else 'NCCL'))},
             'e2e': {'value': e2e_ips, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches_per_step * args.steps,
             'clocks': sampler.summary() if sampler else None,

@@ -172,6 +172,11 @@ SIMCLR_API int simclr_bn_bwd_apply(const void* dz, int dtype, const void* y, int
                                    const double* sums_local, double count, float* dgamma, float* dbeta,
                                    float* coef_ws /* scratch [3][C] */, const float* mask_scale,
                                    const float* mask_shift, void* stream);
+/* The element-wise pass of simclr_bn_bwd_apply alone, with coef [3][C] already computed
+ * (by simclr_comm_bn_bwd_coef: SyncBN statistics exchanged over peer memory). */
+SIMCLR_API int simclr_bn_bwd_apply_coef(const void* dz, int dtype, const void* y, int y_dtype, void* dy,
+                                        int dy_dtype, int64_t rows, int64_t C, const float* coef,
+                                        const float* mask_scale, const float* mask_shift, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Pooling  (tf2/resnet.py:605-611 MaxPooling2D(3,2,'SAME'); :693-696 mean)
@@ -214,6 +219,25 @@ SIMCLR_API int simclr_conv2d_dgrad_tc(const void* dy, const void* wd, void* dx, 
 SIMCLR_API int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, int64_t N,
                                       int64_t H, int64_t W, int64_t Cs, int64_t Cin, int64_t Cout, int64_t R,
                                       int64_t S, int64_t stride, void* stream);
+
+/* BF16x3 -- the tensor-core VERIFICATION mode (fp32 storage, 1e-3 step parity with the fp32
+ * reference of tf2/run.py:557-622 on the tcgen05 pipe).  Every fp32 operand v is split
+ * hi = bf16(v), lo = bf16(v - hi) (`simclr_split_bf16x2`, `simclr_pack_conv_weight` for the hi part
+ * and `simclr_pack_conv_weight_lo` for the residual part of the packed weights, same layouts) and a
+ * product is taken as hi*hi + hi*lo + lo*hi: three exact-product / fp32-accumulate GEMMs summed in
+ * fp32 (TMA reduce-add).  Outputs are fp32 and overwritten. */
+SIMCLR_API int simclr_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream);
+SIMCLR_API int simclr_pack_conv_weight_lo(const float* w_hwio, void* wf_lo, void* wd_lo, int64_t R, int64_t S,
+                                          int64_t Cin, int64_t Cs, int64_t Cout, int64_t Kp, void* stream);
+SIMCLR_API int simclr_conv2d_fprop_tc3(const void* x_hi, const void* x_lo, const void* wf_hi, const void* wf_lo,
+                                       float* y, int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cout,
+                                       int64_t R, int64_t S, int64_t stride, void* stream);
+SIMCLR_API int simclr_conv2d_dgrad_tc3(const void* dy_hi, const void* dy_lo, const void* wd_hi, const void* wd_lo,
+                                       float* dx, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                                       int64_t R, int64_t S, int64_t stride, void* stream);
+SIMCLR_API int simclr_conv2d_wgrad_tc3(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo,
+                                       float* dw, int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cin,
+                                       int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream);
 
 /* CUDA-core fp32 engine reading the fp32 HWIO master directly (verification
  * engine for the tcgen05 path; not the default). */
@@ -290,6 +314,43 @@ SIMCLR_API int simclr_augment(const uint8_t* src, const int64_t* src_offset, con
                               const int32_t* box, const uint8_t* flip, const float* colour, float* out,
                               int64_t n, int64_t height, int64_t width, int64_t out_pixel_stride,
                               int64_t out_channel_offset, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Collectives over NVLink peer memory, fused into the kernels that consume them (no NCCL on these
+ * paths).  Every rank owns one allocation of identical layout that all peers have
+ * mapped ("symmetric memory"); `peer_bufs_dev` is a DEVICE array of `world` base pointers (entry
+ * `rank` is the local one), the remaining arguments are byte offsets into that allocation, the
+ * same on every rank.  `seq_dev` is a device uint64 (initialised to 1, identical on every rank)
+ * that the kernel advances by one per call: the calls are CUDA-graph capturable and must be issued
+ * in the same order on every rank.  A peer that does not show up within 20 s traps the kernel.
+ *
+ * SyncBatchNormalization (tf2/resnet.py:54-60): sums [2][C] doubles of THIS replica ->
+ * one-shot exchange (region data_off + ((seq % nslot)*world + rank)*slot_bytes of every peer,
+ * flags u64 [nslot][world] at flag_off) -> global statistics, summed in rank order, then the
+ * arithmetic of simclr_bn_finalize / the coefficient kernel of simclr_bn_bwd_apply. */
+SIMCLR_API int simclr_comm_bn_finalize(const double* sums_local, double count_local, const float* gamma,
+                                       const float* beta, float eps, float momentum, float* moving_mean,
+                                       float* moving_var, float* mean, float* rstd, float* scale,
+                                       float* shift, int64_t C, const void* peer_bufs_dev, int rank,
+                                       int world, int64_t data_off, int64_t flag_off, int nslot,
+                                       int64_t slot_bytes, void* seq_dev, void* stream);
+/* coef [3][C]: dy = coef0*dz + coef1*y + coef2 from the GLOBAL (sum dz, sum dz*xhat); dgamma / dbeta
+ * receive this replica's sums (the gradient all-reduce adds the replicas). */
+SIMCLR_API int simclr_comm_bn_bwd_coef(const double* sums_local, double count_local, const float* mean,
+                                       const float* rstd, const float* gamma, float* coef, float* dgamma,
+                                       float* dbeta, int64_t C, const void* peer_bufs_dev, int rank,
+                                       int world, int64_t data_off, int64_t flag_off, int nslot,
+                                       int64_t slot_bytes, void* seq_dev, void* stream);
+/* tpu_cross_replica_concat (tf2/objective.py:92-127) as pushes: `nbytes` of `src` land in region
+ * data_off + rank*chunk_stride_bytes of every peer; on return (stream order) the `world` regions at
+ * data_off of the LOCAL allocation hold all ranks' rows, rank-major.  flags u64 [world] at flag_off;
+ * `arrive_dev`: a zeroed device uint32 private to this channel.  One region per channel: the caller
+ * must not start gather t+1 of a channel before every rank has consumed gather t (in the training
+ * step the gradient collective that ends every step guarantees it). */
+SIMCLR_API int simclr_comm_all_gather(const void* src, int64_t nbytes, const void* peer_bufs_dev, int rank,
+                                      int world, int64_t data_off, int64_t flag_off,
+                                      int64_t chunk_stride_bytes, void* seq_dev, void* arrive_dev,
+                                      void* stream);
 
 #ifdef __cplusplus
 }

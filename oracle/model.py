@@ -9,6 +9,7 @@ import torch.nn.functional as F
 
 from . import resnet as resnet_lib
 from . import data_util
+from .bf16_emul import q, qb, qw      # identities unless `emulate_bf16()` is active
 
 
 def get_train_steps(cfg, num_examples):
@@ -48,13 +49,16 @@ class LinearLayer:
                                             center=use_bias) if use_bn else None)
         self.cout = num_classes
 
-    def __call__(self, P, S, x, training):
+    def __call__(self, P, S, x, training, fp32_out=False):
+        # `fp32_out` only matters under bf16-storage emulation: the CUDA path keeps the last projection
+        # layer and the supervised logits in fp32 (their gradient is still handed to wgrad in bf16).
         assert x.dim() == 2
-        x = x @ P[self.kernel]
+        x = qb(x) @ qw(P[self.kernel])
+        x = qb(x) if fp32_out else q(x)
         if self.bias is not None:
             x = x + P[self.bias]
         if self.bn is not None:
-            x = self.bn(P, S, x, training)
+            x = self.bn(P, S, x, training, store=False)    # BN (+ReLU) output is rounded by the caller
         return x
 
 
@@ -88,9 +92,10 @@ class ProjectionHead:
             raise ValueError("only proj_head_mode='nonlinear' is callable (reference quirk Q1)")
         hiddens_list = [x]
         for j in range(cfg.num_proj_layers):
-            h = self.linear_layers[j](P, S, hiddens_list[-1], training)
-            if j != cfg.num_proj_layers - 1:
-                h = F.relu(h)
+            last = j == cfg.num_proj_layers - 1
+            h = self.linear_layers[j](P, S, hiddens_list[-1], training, fp32_out=last)
+            if not last:
+                h = q(F.relu(h))
             hiddens_list.append(h)
         return hiddens_list[-1], hiddens_list[cfg.ft_proj_selector]
 
@@ -102,7 +107,7 @@ class SupervisedHead:
         self.linear_layer = LinearLayer(vs, cfg, 'head_supervised', cin, num_classes)
 
     def __call__(self, P, S, x, training):
-        return self.linear_layer(P, S, x, training)
+        return self.linear_layer(P, S, x, training, fp32_out=True)
 
 
 class Model:

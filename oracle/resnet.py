@@ -17,6 +17,8 @@ import math
 import torch
 import torch.nn.functional as F
 
+from .bf16_emul import q, qb, qw, enabled as _bf16_emulated   # identities unless `emulate_bf16()` is active
+
 BATCH_NORM_EPSILON = 1e-5  # tf2/resnet.py:28
 
 
@@ -99,8 +101,9 @@ class BatchNormRelu:
         self.mm = vs.add(pre + '/moving_mean:0', (channels,), 'zeros', False)
         self.mv = vs.add(pre + '/moving_variance:0', (channels,), 'ones', False)
 
-    def __call__(self, P, S, x, training):
-        # x: [N, C, H, W] or [N, C]
+    def __call__(self, P, S, x, training, store=True):
+        # x: [N, C, H, W] or [N, C].  `store` only matters under bf16-storage emulation: False when
+        # the CUDA path fuses this BN with a following add / ReLU and never materialises its output.
         axes = [0] + list(range(2, x.dim()))
         shape = [1, -1] + [1] * (x.dim() - 2)
         if training:
@@ -120,7 +123,7 @@ class BatchNormRelu:
             y = y + P[self.beta].view(shape)
         if self.relu:
             y = F.relu(y)
-        return y
+        return q(y) if store else y
 
 
 def fixed_padding(x, kernel_size):
@@ -144,11 +147,12 @@ class Conv2dFixedPadding:
         self.cout = filters
 
     def __call__(self, P, S, x, training):
-        w = P[self.kernel].permute(3, 2, 0, 1)  # HWIO -> OIHW
+        w = qw(P[self.kernel]).permute(3, 2, 0, 1)  # HWIO -> OIHW
+        x = qb(x)
         if self.s > 1:
             x = fixed_padding(x, self.k)
-            return F.conv2d(x, w, stride=self.s)
-        return F.conv2d(x, w, padding=(self.k - 1) // 2)
+            return q(F.conv2d(x, w, stride=self.s))
+        return q(F.conv2d(x, w, padding=(self.k - 1) // 2))
 
 
 class PlainConv1x1:
@@ -182,6 +186,7 @@ class SK_Conv2D:
         self.conv1 = PlainConv1x1(vs, scope, mid_dim, 2 * filters)
 
     def __call__(self, P, S, x, training):
+        assert not _bf16_emulated(), 'bf16-storage emulation does not cover SK blocks'
         x = self.conv(P, S, x, training)
         x = self.bn(P, S, x, training)
         streams = torch.stack(torch.split(x, self.filters, dim=1))    # [2,N,f,H,W]
@@ -202,6 +207,7 @@ class SE_Layer:
         self.expand = PlainConv1x1(vs, scope, max(1, int(filters * se_ratio)), cin, True)
 
     def __call__(self, P, S, x, training):
+        assert not _bf16_emulated(), 'bf16-storage emulation does not cover SE blocks'
         t = x.mean(dim=(2, 3), keepdim=True)
         t = self.expand(P, S, F.relu(self.reduce(P, S, t, training)), training)
         return torch.sigmoid(t) * x
@@ -252,10 +258,10 @@ class ResidualBlock:
     def __call__(self, P, S, x, training):
         shortcut = x if self.shortcut is None else self.shortcut(P, S, x, training)
         x = self.b1(P, S, self.c1(P, S, x, training), training)
-        x = self.b2(P, S, self.c2(P, S, x, training), training)
+        x = self.b2(P, S, self.c2(P, S, x, training), training, store=self.se is not None)
         if self.se is not None:
             x = self.se(P, S, x, training)
-        return F.relu(x + shortcut)
+        return q(F.relu(x + shortcut))
 
 
 class BottleneckBlock:
@@ -287,10 +293,10 @@ class BottleneckBlock:
             x = self.sk(P, S, x, training)
         else:
             x = self.b2(P, S, self.c2(P, S, x, training), training)
-        x = self.b3(P, S, self.c3(P, S, x, training), training)
+        x = self.b3(P, S, self.c3(P, S, x, training), training, store=self.se is not None)
         if self.se is not None:
             x = self.se(P, S, x, training)
-        return F.relu(x + shortcut)
+        return q(F.relu(x + shortcut))
 
 
 class BlockGroup:
@@ -358,20 +364,20 @@ class Resnet:
         self.cout = cin
 
     def __call__(self, P, S, x_nhwc, training, endpoints=None):
-        x = x_nhwc.permute(0, 3, 1, 2)
+        x = q(x_nhwc.permute(0, 3, 1, 2))      # (emulation: the network input is cast to bf16)
         for layer in self.stem:
             x = layer(P, S, x, training)
             if endpoints is not None and isinstance(layer, Conv2dFixedPadding):
                 endpoints['initial_conv'] = x
         if not self.cifar_stem:
-            x = max_pool_3x3_s2_same(x)
+            x = qb(max_pool_3x3_s2_same(x))
         if endpoints is not None:
             endpoints['initial_max_pool'] = x
         for i, g in enumerate(self.groups):
             x = g(P, S, x, training)
             if endpoints is not None:
                 endpoints['block_group%d' % (i + 1)] = x
-        x = x.mean(dim=(2, 3))                                  # :693-696
+        x = q(x.mean(dim=(2, 3)))                               # :693-696
         if endpoints is not None:
             endpoints['final_avg_pool'] = x
         return x

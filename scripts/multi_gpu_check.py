@@ -13,6 +13,7 @@ from oracle import model as OM, step as OS
 precision = sys.argv[1] if len(sys.argv) > 1 else 'fp32'
 conv_engine = sys.argv[2] if len(sys.argv) > 2 else 'simt'
 global_bn = (sys.argv[3] != 'local') if len(sys.argv) > 3 else True
+check_graph = len(sys.argv) > 4 and sys.argv[4] == 'graph'     # also: 2 graph replays == 2 eager steps
 flags_def.FLAGS(['multi'])
 rank = run.init_distributed()
 R = dist.get_world_size()
@@ -41,6 +42,7 @@ if rank == 0:
     info = OS.forward_backward(om, P, S_, feats, labs, blur_draws=draws)
     job_loss = float(lt.item()) / R
     res = {'world': R, 'precision': precision, 'engine': conv_engine, 'global_bn': global_bn,
+           'collectives': 'peer' if trainer.strategy.comm is not None else 'nccl',
            'loss': job_loss, 'oracle_loss': float(info['loss'])}
     tol = 1e-3 if precision == 'fp32' and conv_engine == 'simt' else 0.5
     worst, wname = 0.0, ''
@@ -66,6 +68,28 @@ dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
     print('MULTI_GPU_WEIGHTS_IDENTICAL %d' % int(t.item()), flush=True)
     ok = ok and t.item() == 1.0
+if check_graph:
+    # segmented CUDA-graph replay at R > 1 (forward+backward graph | NCCL all-reduce | LARS graph) against eager steps
+    vs, opt = trainer.model.vs, trainer.optimizer
+    snap = (vs.flat_value.clone(), vs.flat_moving.clone(), opt._flat_v.clone(), opt.iterations)
+    f_dev, l_dev = feats[rank].cuda(), labs[rank].cuda()
+    for _ in range(2):
+        trainer.single_step(f_dev, l_dev)
+    torch.cuda.synchronize()
+    w_eager = vs.flat_value.clone()
+    vs.flat_value.copy_(snap[0]); vs.flat_moving.copy_(snap[1]); opt._flat_v.copy_(snap[2]); opt.iterations = snap[3]
+    trainer.capture(f_dev, l_dev, warmup=1, restore=True)
+    for _ in range(2):
+        trainer.replay()
+    torch.cuda.synchronize()
+    err = rel_err(vs.flat_value, w_eager)
+    w0 = vs.flat_value.clone(); dist.broadcast(w0, 0)
+    t = torch.tensor([1.0 if torch.equal(vs.flat_value, w0) else 0.0], device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        g_ok = err < 2e-3 and t.item() == 1.0
+        print('MULTI_GPU_GRAPH ' + json.dumps({'replay_vs_eager_rel_err': err, 'ranks_identical': bool(t.item() == 1.0), 'ok': bool(g_ok)}), flush=True)
+        ok = ok and g_ok
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -481,22 +481,11 @@ int simclr_bn_bwd_relu_reduce(const void* dz, int dtype, const void* y, int y_dt
   return SIMCLR_ERR_INVALID_ARG;
 }
 
-int simclr_bn_bwd_apply(const void* dz, int dtype, const void* y, int y_dtype, void* dy, int dy_dtype,
-                        int64_t rows, int64_t C, const float* mean, const float* rstd, const float* gamma,
-                        const double* sums, const double* sums_local, double count, float* dgamma,
-                        float* dbeta, float* coef_ws, const float* mask_scale, const float* mask_shift,
-                        void* stream) {
-  SIMCLR_CHECK_ARG((mask_scale == nullptr) == (mask_shift == nullptr), "bn_bwd_apply: mask_scale and mask_shift go together");
-  SIMCLR_CHECK_ARG(dz && y && dy && mean && rstd && sums && sums_local && coef_ws, "bn_bwd_apply: null pointer");
-  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && count > 0, "bn_bwd_apply: bad shape");
-  SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(y) && aligned16(dy), "bn_bwd_apply: alignment");
+static int launch_bwd_apply(const void* dz, int dtype, const void* y, int y_dtype, void* dy, int dy_dtype, int64_t rows,
+                            int64_t C, const float* coef_ws, const float* mask_scale, const float* mask_shift,
+                            cudaStream_t st) {
   const int64_t nvec = rows * C / 8;
-  cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = ew_grid_c(nvec, C);
-  SIMCLR_CHECK_ARG(aligned16(coef_ws), "bn_bwd_apply: coef_ws alignment");
-  bn_bwd_coef_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(mean, rstd, gamma, sums, sums_local, 1.0 / count,
-                                                                   coef_ws, dgamma, dbeta, (int)C);
-  SIMCLR_CHECK_LAUNCH();
 #define LAUNCH(T, Ty, Td)                                                                                          \
   do {                                                                                                             \
     if (mask_scale) bn_bwd_apply_kernel<T, Ty, Td, true><<<grid, BT, 0, st>>>((const T*)dz, (const Ty*)y, (Td*)dy, nvec, (int)C, coef_ws, mask_scale, mask_shift); \
@@ -517,6 +506,33 @@ int simclr_bn_bwd_apply(const void* dz, int dtype, const void* y, int y_dtype, v
 #undef LAUNCH
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
+}
+
+int simclr_bn_bwd_apply(const void* dz, int dtype, const void* y, int y_dtype, void* dy, int dy_dtype,
+                        int64_t rows, int64_t C, const float* mean, const float* rstd, const float* gamma,
+                        const double* sums, const double* sums_local, double count, float* dgamma,
+                        float* dbeta, float* coef_ws, const float* mask_scale, const float* mask_shift,
+                        void* stream) {
+  SIMCLR_CHECK_ARG((mask_scale == nullptr) == (mask_shift == nullptr), "bn_bwd_apply: mask_scale and mask_shift go together");
+  SIMCLR_CHECK_ARG(dz && y && dy && mean && rstd && sums && sums_local && coef_ws, "bn_bwd_apply: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && count > 0, "bn_bwd_apply: bad shape");
+  SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(y) && aligned16(dy), "bn_bwd_apply: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  SIMCLR_CHECK_ARG(aligned16(coef_ws), "bn_bwd_apply: coef_ws alignment");
+  bn_bwd_coef_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(mean, rstd, gamma, sums, sums_local, 1.0 / count,
+                                                                   coef_ws, dgamma, dbeta, (int)C);
+  SIMCLR_CHECK_LAUNCH();
+  return launch_bwd_apply(dz, dtype, y, y_dtype, dy, dy_dtype, rows, C, coef_ws, mask_scale, mask_shift, st);
+}
+
+int simclr_bn_bwd_apply_coef(const void* dz, int dtype, const void* y, int y_dtype, void* dy, int dy_dtype,
+                             int64_t rows, int64_t C, const float* coef, const float* mask_scale,
+                             const float* mask_shift, void* stream) {
+  SIMCLR_CHECK_ARG((mask_scale == nullptr) == (mask_shift == nullptr), "bn_bwd_apply_coef: mask_scale and mask_shift go together");
+  SIMCLR_CHECK_ARG(dz && y && dy && coef, "bn_bwd_apply_coef: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_bwd_apply_coef: bad shape");
+  SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(y) && aligned16(dy) && aligned16(coef), "bn_bwd_apply_coef: alignment");
+  return launch_bwd_apply(dz, dtype, y, y_dtype, dy, dy_dtype, rows, C, coef, mask_scale, mask_shift, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -115,7 +115,24 @@ __global__ void add_inplace_kernel(T* __restrict__ a, const T* __restrict__ b, i
 // wd [Cin][Kdp] (k=(r*S+s)*Cout+co, zero padded to the K block).
 // bf16 with 4 stored channels (the stem): k = (r*(S+1) + s+1)*4 + c, slot s' = 0 of every filter
 // row zero -- S+1 slots make a filter row a whole number of 16-byte pixel pairs.
-template <typename T>
+// PART 0: the value itself; PART 1 (bf16 only): the residual v - bf16(v) of the BF16x3 split
+template <typename T, int PART> __device__ __forceinline__ T pack_part(float v) {
+  if (PART == 0) return from_f<T>(v);
+  return from_f<T>(v - __bfloat162float(__float2bfloat16_rn(v)));
+}
+
+// x fp32 -> hi = bf16(x), lo = bf16(x - hi): x = hi + lo up to 2^-17 |x| (BF16x3 operands)
+__global__ void split_bf16x2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+template <typename T, int PART = 0>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int R,
                                    int S, int Cin, int Cs, int Cout, int Kp, int Kdp) {
   const int64_t nf = (int64_t)Cout * Kp;
@@ -131,12 +148,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
       } else if (tap < R * S && c < Cin) {
         v = w[((int64_t)tap * Cin + c) * Cout + co];
       }
-      wf[i] = from_f<T>(v);
+      wf[i] = pack_part<T, PART>(v);
     } else {
       const int64_t j = i - nf;
       const int ci = (int)(j / Kdp), k = (int)(j % Kdp);
       const int tap = k / Cout, co = k % Cout;
-      wd[j] = from_f<T>(tap < R * S ? w[((int64_t)tap * Cin + ci) * Cout + co] : 0.f);
+      wd[j] = pack_part<T, PART>(tap < R * S ? w[((int64_t)tap * Cin + ci) * Cout + co] : 0.f);
     }
   }
 }
@@ -375,6 +392,26 @@ int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, 
   if (dtype == SIMCLR_BF16) pack_weight_kernel<bf16><<<grid, 256, 0, st>>>(w_hwio, (bf16*)wf, (bf16*)wd, (int)R, (int)S, (int)Cin, (int)Cs, (int)Cout, (int)Kp, (int)Kdp);
   else if (dtype == SIMCLR_F32) pack_weight_kernel<float><<<grid, 256, 0, st>>>(w_hwio, (float*)wf, (float*)wd, (int)R, (int)S, (int)Cin, (int)Cs, (int)Cout, (int)Kp, (int)Kdp);
   else { set_error("pack_conv_weight: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_pack_conv_weight_lo(const float* w_hwio, void* wf_lo, void* wd_lo, int64_t R, int64_t S, int64_t Cin,
+                               int64_t Cs, int64_t Cout, int64_t Kp, void* stream) {
+  SIMCLR_CHECK_ARG(w_hwio && wf_lo, "pack_conv_weight_lo: null pointer");
+  SIMCLR_CHECK_ARG(R > 0 && S > 0 && Cin > 0 && Cs >= Cin && Cout > 0 && Kp % 64 == 0, "pack_conv_weight_lo: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t Kdp = (R * S * Cout + 63) / 64 * 64;
+  const int64_t total = Cout * Kp + (wd_lo ? Cin * Kdp : 0);
+  pack_weight_kernel<bf16, 1><<<grid_for(total, 256), 256, 0, st>>>(w_hwio, (bf16*)wf_lo, (bf16*)wd_lo, (int)R, (int)S,
+                                                                     (int)Cin, (int)Cs, (int)Cout, (int)Kp, (int)Kdp);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+  SIMCLR_CHECK_ARG(x && hi && lo && n > 0, "split_bf16x2: bad arguments");
+  split_bf16x2_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)hi, (bf16*)lo, n);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }

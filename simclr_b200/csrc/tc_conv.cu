@@ -59,6 +59,7 @@ struct Geom {
   // TMA im2col feed of the gathered operand: base pixel of GEMM row (n, p, q) is
   // (q*stride + im_base, p*stride + im_base); the tap goes into the instruction's filter offsets
   int im2col, im_base, im_nimg;
+  int accum;           // fp32 outputs only: add into `out` (TMA reduce-add / atomics) instead of storing (BF16x3 passes)
 };
 
 template <typename T> struct Elt;
@@ -259,7 +260,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             fence_proxy_async();
             named_barrier_sync(1, EPI_THREADS);
             if (threadIdx.x == 0) {
-              tma_store_2d(&tmap_out, stage, n0, tm * 128); tma_store_commit();
+              if (sizeof(To) == 4 && g.accum) tma_reduce_add_2d(&tmap_out, stage, n0, tm * 128);
+              else tma_store_2d(&tmap_out, stage, n0, tm * 128);
+              tma_store_commit();
               if (STATS_WARPS) mbar_arrive(&ctl.sfull[box_ctr & 1]);
             }
             if (STATS && !STATS_WARPS) {
@@ -333,7 +336,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           tmem_ld_wait();
           const int n0 = tn * BN + c * 32;
           const int valid = g.n_out - n0;
-          if (m < g.M && valid > 0) store_row32<To>(out + row_off + n0, acc, valid, vec_ok);
+          if (m < g.M && valid > 0) {
+            if (sizeof(To) == 4 && g.accum) {
+              float* o = reinterpret_cast<float*>(out) + row_off + n0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < valid) atomicAdd(o + i, __uint_as_float(acc[i]));
+            } else {
+              store_row32<To>(out + row_off + n0, acc, valid, vec_ok);
+            }
+          }
         }
         tc_fence_before();
         warp_arrive(&ctl.tmem_empty[as]);
@@ -942,9 +953,10 @@ inline StemGeom stem_geom(bool smallc, int mode, int64_t W, int64_t S, int64_t s
 //   gathered tensor [N][Hs][Ws][Cs]; GEMM rows = N*P*Q; weights wk [n_out][Kp]
 int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, int out_dtype, int64_t N, int64_t Hs,
               int64_t Ws, int64_t Cs, int64_t P, int64_t Q, int64_t n_out, int64_t R, int64_t S, int64_t stride,
-              cudaStream_t st, const char* what, double* bn_sums = nullptr) {
+              cudaStream_t st, const char* what, double* bn_sums = nullptr, bool accum = false) {
   const int es = dtype == SIMCLR_BF16 ? 2 : 4;
   const int KBE = 128 / es, CH = 16 / es;
+  if (accum && (out_dtype != SIMCLR_F32 || bn_sums)) { set_error("%s: accumulation needs fp32 outputs and no fused statistics", what); return SIMCLR_ERR_INVALID_ARG; }
   bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);
   if (!(Cs % CH == 0 || smallc)) { set_error("%s: stored channels (%lld) must be a multiple of %d", what, (long long)Cs, CH); return SIMCLR_ERR_UNSUPPORTED; }
   if (smallc && mode != 0) { set_error("%s: 4-channel tensors are only supported as the conv input", what); return SIMCLR_ERR_UNSUPPORTED; }
@@ -974,7 +986,7 @@ int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, i
   g.Cin = g.Cout = 0; g.splits = 1; g.kb_per_split = g.num_kb;
   g.use_tab = 0; g.cblocks = 1; g.os = 0; g.oh0 = g.ow0 = 0; g.OH = g.OW = 0;
   g.tap_sign = mode == 0 ? 1 : -1;
-  g.im2col = 0; g.im_base = 0; g.im_nimg = (int)N;
+  g.im2col = 0; g.im_base = 0; g.im_nimg = (int)N; g.accum = accum ? 1 : 0;
   // plain GEMM (1x1, stride 1, no padding): activations go through TMA as well
   bool a_tma = (R == 1 && S == 1 && stride == 1 && !smallc && (Cs * es) % 16 == 0);
   CUtensorMap ta, tb, tout;
@@ -1015,9 +1027,11 @@ int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, i
 // own tap list -- no multiplications by structural zeros (a stride-2 3x3 does 9/4 of the dense
 // work instead of 9x).  Classes without taps (1x1 kernels) stay zero from the memset.
 int run_dgrad_strided(const void* dy, const void* wd, void* dx, int dtype, int out_dtype, int64_t N, int64_t H,
-                      int64_t W, int64_t Cin, int64_t Cout, int64_t R, int64_t S, int64_t stride, cudaStream_t st) {
+                      int64_t W, int64_t Cin, int64_t Cout, int64_t R, int64_t S, int64_t stride, cudaStream_t st,
+                      bool accum = false) {
   const int es = dtype == SIMCLR_BF16 ? 2 : 4;
   const int eo = out_dtype == SIMCLR_BF16 ? 2 : 4;
+  if (accum && out_dtype != SIMCLR_F32) { set_error("conv2d_dgrad_tc: accumulation needs fp32 outputs"); return SIMCLR_ERR_INVALID_ARG; }
   const int KBE = 128 / es;
   const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const int pad_h = (int)((R - 1) / 2), pad_w = (int)((S - 1) / 2);
@@ -1037,7 +1051,7 @@ int run_dgrad_strided(const void* dy, const void* wd, void* dx, int dtype, int o
     for (int s2 = 0; s2 < S; ++s2) if ((pw + pad_w - s2) % (int)stride == 0) ++cnt;
     if (cnt == 0) need_zero = true;
   }
-  if (need_zero) SIMCLR_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)(N * H * W * Cin) * eo, st));
+  if (need_zero && !accum) SIMCLR_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)(N * H * W * Cin) * eo, st));
   for (int ph = 0; ph < stride; ++ph) {
     for (int pw = 0; pw < stride; ++pw) {
       Geom g;
@@ -1070,7 +1084,7 @@ int run_dgrad_strided(const void* dy, const void* wd, void* dx, int dtype, int o
       g.tap_sign = 1;
       g.use_tab = 1; g.os = (int)stride; g.oh0 = ph; g.ow0 = pw; g.OH = (int)H; g.OW = (int)W;
       // the class is a stride-1 walk over the dY grid: TMA im2col when its pixel grid is the dY grid
-      g.im2col = 0; g.im_base = 0; g.im_nimg = (int)N;
+      g.im2col = 0; g.im_base = 0; g.im_nimg = (int)N; g.accum = accum ? 1 : 0;
       CUtensorMap ta = tb;
       bool a_tma = false;
       if (im2col_enabled() && get_encode_im2col() != nullptr && P2 == Ho && Q2 == Wo && Ho < 32768 && Wo < 32768) {
@@ -1164,8 +1178,9 @@ int simclr_conv2d_dgrad_tc(const void* dy, const void* wd, void* dx, int dtype, 
                        "conv2d_dgrad_tc");
 }
 
-int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, int64_t N, int64_t H, int64_t W,
-                           int64_t Cs, int64_t Cin, int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream) {
+static int wgrad_tc_impl(const void* x, const void* dy, float* dw, int dtype, int64_t N, int64_t H, int64_t W,
+                         int64_t Cs, int64_t Cin, int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream,
+                         bool zero) {
   using namespace simclr::tc;
   SIMCLR_CHECK_ARG(x && dy && dw, "conv2d_wgrad_tc: null pointer");
   SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cs >= Cin && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
@@ -1206,7 +1221,7 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   g.num_kb = (int)((M + pxs - 1) / pxs);
   g.tiles_m = (int)((R * Sk * Cs + 127) / 128); g.tiles_n = (int)((Cout + bn - 1) / bn);
   g.Cin = (int)Cin; g.Cout = (int)Cout;
-  g.use_tab = 0; g.cblocks = 1; g.os = 0; g.oh0 = g.ow0 = 0; g.OH = g.OW = 0; g.tap_sign = 1;
+  g.use_tab = 0; g.cblocks = 1; g.os = 0; g.oh0 = g.ow0 = 0; g.OH = g.OW = 0; g.tap_sign = 1; g.accum = 0;
   const int tiles = g.tiles_m * g.tiles_n;
   int splits = (2 * num_sms() + tiles - 1) / tiles;
   const int max_splits = g.num_kb / 8 > 0 ? g.num_kb / 8 : 1;
@@ -1234,10 +1249,79 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
   const bool tma_red = !stem && Cs == Cin && aligned16(dw) && (Cout * 4) % 16 == 0;
   if (tma_red) { rc = make_tmap_2d(&tdw, dw, 4, (uint64_t)(R * S * Cin), (uint64_t)Cout, (uint64_t)Cout * 4, 128, 32); if (rc) return rc; }
   else tdw = tdy;
-  SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(R * S * Cin * Cout) * sizeof(float), st));
+  if (zero) SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(R * S * Cin * Cout) * sizeof(float), st));
   if (dtype == SIMCLR_BF16) return dispatch_wgrad<__nv_bfloat16>(bn, smallc, a_tma, tma_red, tx, tdy, tdw, g, dw, st);
   set_error("conv2d_wgrad_tc: unknown dtype %d", dtype);
   return SIMCLR_ERR_INVALID_ARG;
+}
+
+int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, int64_t N, int64_t H, int64_t W,
+                           int64_t Cs, int64_t Cin, int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream) {
+  return wgrad_tc_impl(x, dy, dw, dtype, N, H, W, Cs, Cin, Cout, R, S, stride, stream, true);
+}
+
+// ---------------------------------------------------------------------------
+// BF16x3: fp32-accurate products on the bf16 tensor pipe.  Every fp32 operand is split as
+// v = hi + lo (+ 2^-17 |v|), hi = bf16(v), lo = bf16(v - hi); a product a*b is taken as
+// a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (the dropped lo*lo term is 2^-16 relative), each of the three
+// an exact-product / fp32-accumulate tcgen05 GEMM, summed in fp32 at L2 (TMA reduce-add).  This
+// is the tensor-core verification mode: fp32 storage, 1e-3 step parity with the fp32 reference.
+// ---------------------------------------------------------------------------
+int simclr_conv2d_fprop_tc3(const void* x_hi, const void* x_lo, const void* wf_hi, const void* wf_lo, float* y,
+                            int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cout, int64_t R, int64_t S,
+                            int64_t stride, void* stream) {
+  SIMCLR_CHECK_ARG(x_hi && x_lo && wf_hi && wf_lo && y, "conv2d_fprop_tc3: null pointer");
+  SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cs > 0 && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
+                   "conv2d_fprop_tc3: bad geometry");
+  const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const void* xs[3] = {x_hi, x_hi, x_lo};
+  const void* ws[3] = {wf_hi, wf_lo, wf_hi};
+  for (int p = 0; p < 3; ++p) {
+    int rc = tc::run_igemm(0, xs[p], ws[p], y, SIMCLR_BF16, SIMCLR_F32, N, H, W, Cs, Ho, Wo, Cout, R, S, stride,
+                           (cudaStream_t)stream, "conv2d_fprop_tc3", nullptr, p > 0);
+    if (rc) return rc;
+  }
+  return SIMCLR_OK;
+}
+
+int simclr_conv2d_dgrad_tc3(const void* dy_hi, const void* dy_lo, const void* wd_hi, const void* wd_lo, float* dx,
+                            int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t R, int64_t S,
+                            int64_t stride, void* stream) {
+  SIMCLR_CHECK_ARG(dy_hi && dy_lo && wd_hi && wd_lo && dx, "conv2d_dgrad_tc3: null pointer");
+  SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
+                   "conv2d_dgrad_tc3: bad geometry");
+  const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const void* ds[3] = {dy_hi, dy_hi, dy_lo};
+  const void* ws[3] = {wd_hi, wd_lo, wd_hi};
+  for (int p = 0; p < 3; ++p) {
+    int rc;
+    if (stride > 1) {
+      if (!(stride <= 3 && Cout % 64 == 0 && simclr::aligned16(ds[p]) && simclr::aligned16(ws[p]) && simclr::aligned16(dx))) {
+        simclr::set_error("conv2d_dgrad_tc3: stride %lld needs Cout %% 64 == 0, stride <= 3 and 16-byte aligned operands", (long long)stride);
+        return SIMCLR_ERR_UNSUPPORTED;
+      }
+      rc = tc::run_dgrad_strided(ds[p], ws[p], dx, SIMCLR_BF16, SIMCLR_F32, N, H, W, Cin, Cout, R, S, stride,
+                                 (cudaStream_t)stream, p > 0);
+    } else {
+      rc = tc::run_igemm(1, ds[p], ws[p], dx, SIMCLR_BF16, SIMCLR_F32, N, Ho, Wo, Cout, H, W, Cin, R, S, stride,
+                         (cudaStream_t)stream, "conv2d_dgrad_tc3", nullptr, p > 0);
+    }
+    if (rc) return rc;
+  }
+  return SIMCLR_OK;
+}
+
+int simclr_conv2d_wgrad_tc3(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw,
+                            int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cin, int64_t Cout, int64_t R,
+                            int64_t S, int64_t stride, void* stream) {
+  SIMCLR_CHECK_ARG(x_hi && x_lo && dy_hi && dy_lo && dw, "conv2d_wgrad_tc3: null pointer");
+  const void* xs[3] = {x_hi, x_hi, x_lo};
+  const void* ds[3] = {dy_hi, dy_lo, dy_hi};
+  for (int p = 0; p < 3; ++p) {
+    int rc = wgrad_tc_impl(xs[p], ds[p], dw, SIMCLR_BF16, N, H, W, Cs, Cin, Cout, R, S, stride, stream, p == 0);
+    if (rc) return rc;
+  }
+  return SIMCLR_OK;
 }
 
 }  // extern "C"

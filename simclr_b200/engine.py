@@ -120,7 +120,7 @@ def _init_tensor(shape, init, g):
 class ReplicaContext:
     """Stand-in for `tf.distribute` replica context / strategy: one process per GPU."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, peer_comm=True):
         if dist.is_available() and dist.is_initialized():
             self.num_replicas_in_sync = dist.get_world_size(group)
             self.replica_id = dist.get_rank(group)
@@ -128,17 +128,26 @@ class ReplicaContext:
             self.num_replicas_in_sync = 1
             self.replica_id = 0
         self.group = group
+        # NVLink peer-memory collectives (csrc/comm.cu); None -> NCCL carries the same collectives
+        self.comm = None
+        if peer_comm and self.num_replicas_in_sync > 1 and torch.cuda.is_available() and \
+                dist.get_backend(group) == 'nccl':
+            from .comm import PeerComm
+            self.comm = PeerComm.create(group)
 
     def all_reduce_sum(self, t):
         if self.num_replicas_in_sync > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
-    def all_gather(self, t):
-        """[...] -> [R, ...] (rank-major)."""
+    def all_gather(self, t, channel=None):
+        """[...] -> [R, ...] (rank-major).  `channel`: name of a peer-memory gather region ('z',
+        'lse'); without one (or without peer memory) the gather goes through NCCL."""
         R = self.num_replicas_in_sync
         if R == 1:
             return t.unsqueeze(0)
+        if self.comm is not None and channel is not None:
+            return self.comm.all_gather(t, channel)
         t = t.contiguous()
         out = torch.empty((R * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, t, group=self.group)      # concatenation along dim 0
@@ -156,6 +165,8 @@ class Engine:
         precision = precision or FLAGS.b200_precision
         self.act_dtype = torch.bfloat16 if precision == 'bf16' else torch.float32
         self.conv_engine = conv_engine or FLAGS.b200_conv_engine
+        if self.conv_engine == 'tc3' and self.act_dtype != torch.float32:
+            raise ValueError("b200_conv_engine='tc3' (BF16x3) is the fp32-storage mode: use --b200_precision=fp32")
         self.ctx = ctx or ReplicaContext()
         self.profile = None        # list of per-launch (kind, shape, flops, ev0, ev1) when profiling
 

@@ -89,8 +89,10 @@ def define_flags():
     f.DEFINE_enum('b200_precision', 'bf16', ['bf16', 'fp32'],
                   'Activation/operand storage type of the conv stack: bf16 (tcgen05 kind::f16, '
                   'fp32 accumulate) or fp32 (parity mode).')
-    f.DEFINE_enum('b200_conv_engine', 'tc', ['tc', 'simt'],
-                  'tc: tcgen05/TMA implicit GEMM (default). simt: CUDA-core fp32 verification engine.')
+    f.DEFINE_enum('b200_conv_engine', 'tc', ['tc', 'tc3', 'simt'],
+                  'tc: tcgen05/TMA implicit GEMM (default). tc3: BF16x3 split products on the tcgen05 engine '
+                  '(fp32 storage, fp32-accurate: the tensor-core verification mode). '
+                  'simt: CUDA-core fp32 verification engine.')
     f.DEFINE_integer('b200_num_classes', 1000, 'Classes of the supervised head when no dataset is read.')
     f.DEFINE_integer('b200_num_examples', 1281167, 'Examples per epoch when no dataset is read.')
 

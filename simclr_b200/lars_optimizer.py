@@ -104,12 +104,19 @@ class LARSOptimizer:
         if self._tables is None or self._tables['names'] != [v.name for v in variables]:
             self._build(variables)
         T = self._tables
-        if not torch.cuda.is_current_stream_capturing():
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
             self.stage_learning_rate()       # inside a graph capture the kernel just reads lr_dev
         lib.lars_apply(T['n'], T['n_chunks'], T['w'], T['g'], T['v'], T['numel'], T['flags'], T['ct'], T['co'],
                        T['begin'], CHUNK_ELEMS, T['lr_dev'], float(self.momentum), float(self.weight_decay),
                        float(self.eeta), T['partials'], stream_ptr())
-        self.iterations += 1
+        if not capturing:                    # a capture records the update, it does not execute one:
+            self.iterations += 1             # `prepare_replay` advances the schedule per replay
+
+    def ensure_built(self, variables):
+        """Builds the pointer tables / momentum slots (host->device copies) ahead of a graph capture."""
+        if self._tables is None or self._tables['names'] != [v.name for v in variables]:
+            self._build(variables)
 
     def stage_learning_rate(self):
         """Writes lr_t -- the schedule at the pre-increment iteration -- into

@@ -51,7 +51,7 @@ def contrastive_forward(hidden, hidden_norm=True, temperature=1.0, strategy=None
     z = e.empty((rows, D), torch.float32)
     inv_norm = e.empty((rows,), torch.float32)
     lib.ntxent_normalize(hidden, rows, D, int(bool(hidden_norm)), z, inv_norm, st)
-    z_all = strategy.all_gather(z) if R > 1 else z            # [R][2][B][D]
+    z_all = strategy.all_gather(z, channel='z') if R > 1 else z            # [R][2][B][D]
     G = R * B
     ws_bytes = lib.ntxent_workspace_bytes(B, R, D)
     ws = e.empty((ws_bytes,), torch.uint8)
@@ -75,7 +75,7 @@ def contrastive_backward(ctx, grad_scale):
     """d(job loss)/d(hidden) for this replica's rows; grad_scale = dL/d(row loss)
     (the step uses 1/(B*R): local mean over B, then loss / num_replicas, tf2/run.py:617)."""
     e = get_engine()
-    lse_all = ctx.strategy.all_gather(ctx.lse) if ctx.R > 1 else ctx.lse     # [R][2][B]
+    lse_all = ctx.strategy.all_gather(ctx.lse, channel='lse') if ctx.R > 1 else ctx.lse     # [R][2][B]
     dhidden = e.empty((2 * ctx.B, ctx.D), torch.float32)
     lib.ntxent_backward(ctx.z_all, lse_all, ctx.inv_norm, int(ctx.hidden_norm), ctx.B, ctx.R, ctx.D, ctx.rid,
                         ctx.temperature, float(grad_scale), dhidden, ctx.ws, ctx.ws_bytes, stream_ptr())

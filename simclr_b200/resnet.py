@@ -12,7 +12,7 @@ blocks (`se_ratio > 0`) are on the GPU path.
 """
 import torch
 
-from ._lib import lib, stream_ptr, F32
+from ._lib import lib, stream_ptr, F32, BF16
 from .engine import get_engine, BATCH_NORM_EPSILON
 from .flags_def import FLAGS
 
@@ -50,11 +50,17 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
                 sums = e.empty((2 * C,), torch.float64)
                 lib.bn_stats(y, e.code(y.dtype), rows, C, sums, st)
             count = float(rows)
-            if e.sync_bn:            # SyncBatchNormalization: all-reduce sum x, sum x^2 (C2)
-                e.ctx.all_reduce_sum(sums)
-                count *= e.ctx.num_replicas_in_sync
-            lib.bn_finalize(sums, count, g, b, BATCH_NORM_EPSILON, float(FLAGS.batch_norm_decay),
-                            self.moving_mean.value, self.moving_variance.value, mean, rstd, scale, shift, C, st)
+            if e.sync_bn and e.ctx.comm is not None and 2 * C * 8 <= e.ctx.comm.slot_bytes:
+                # SyncBatchNormalization (C2): one-shot exchange of (sum x, sum x^2) over NVLink peer memory
+                # inside the finalize kernel
+                e.ctx.comm.bn_finalize(sums, count, g, b, BATCH_NORM_EPSILON, float(FLAGS.batch_norm_decay),
+                                       self.moving_mean.value, self.moving_variance.value, mean, rstd, scale, shift, C)
+            else:
+                if e.sync_bn:        # same collective through NCCL
+                    e.ctx.all_reduce_sum(sums)
+                    count *= e.ctx.num_replicas_in_sync
+                lib.bn_finalize(sums, count, g, b, BATCH_NORM_EPSILON, float(FLAGS.batch_norm_decay),
+                                self.moving_mean.value, self.moving_variance.value, mean, rstd, scale, shift, C, st)
         else:
             r = torch.rsqrt(self.moving_variance.value + BATCH_NORM_EPSILON)
             sc = r if g is None else g * r
@@ -92,16 +98,22 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
             lib.bn_bwd_reduce(dz, dz2, zmask, e.code(dz.dtype), y, e.code(y.dtype), rows, C, mean, rstd, sums, st)
             msc = msh = None
         sums_g, count = sums, float(rows)
+        dy = e.empty(y.shape, dy_dtype or e.act_dtype)
+        coef = e.empty((3 * C,), torch.float32)
+        gam = None if self.gamma is None else self.gamma.value
+        dgam = None if self.gamma is None else self.gamma.grad
+        dbet = None if self.beta is None else self.beta.grad
+        if e.sync_bn and e.ctx.comm is not None and 2 * C * 8 <= e.ctx.comm.slot_bytes:
+            e.ctx.comm.bn_bwd_coef(sums, count, mean, rstd, gam, coef, dgam, dbet, C)
+            lib.bn_bwd_apply_coef(dz, e.code(dz.dtype), y, e.code(y.dtype), dy, e.code(dy.dtype), rows, C, coef,
+                                  msc, msh, st)
+            return dy
         if e.sync_bn:
             sums_g = sums.clone()
             e.ctx.all_reduce_sum(sums_g)
             count *= e.ctx.num_replicas_in_sync
-        dy = e.empty(y.shape, dy_dtype or e.act_dtype)
-        coef = e.empty((3 * C,), torch.float32)
         lib.bn_bwd_apply(dz, e.code(dz.dtype), y, e.code(y.dtype), dy, e.code(dy.dtype), rows, C, mean, rstd,
-                         None if self.gamma is None else self.gamma.value, sums_g, sums, count,
-                         None if self.gamma is None else self.gamma.grad,
-                         None if self.beta is None else self.beta.grad, coef, msc, msh, st)
+                         gam, sums_g, sums, count, dgam, dbet, coef, msc, msh, st)
         return dy
 
 
@@ -116,6 +128,7 @@ class ConvOp:
         self.cs = stored_cin or cin
         self.need_dgrad = need_dgrad
         self.wf = self.wd = None
+        self.wf_lo = self.wd_lo = None       # BF16x3: residual parts of the packed weights
         self.saved_x = None
 
     def _pack(self, e):
@@ -130,6 +143,26 @@ class ConvOp:
             self.wd = e.empty((self.cin, (kd + kbe - 1) // kbe * kbe)) if self.need_dgrad else None
         lib.pack_conv_weight(self.kernel.value, self.wf, self.wd, e.code(e.act_dtype), self.R, self.S, self.cin,
                              self.cs, self.cout, Kp, stream_ptr())
+
+    def _pack3(self, e):
+        """BF16x3 operands: hi = bf16(w) in the ordinary packed layouts, lo = bf16(w - hi)."""
+        K = self.R * (self.S + 1 if self.cs == 4 else self.S) * self.cs
+        Kp = (K + 63) // 64 * 64
+        if self.wf is None or self.wf.dtype != torch.bfloat16 or self.wf_lo is None:
+            kd = (self.R * self.S * self.cout + 63) // 64 * 64
+            self.wf = e.empty((self.cout, Kp), torch.bfloat16)
+            self.wf_lo = e.empty((self.cout, Kp), torch.bfloat16)
+            self.wd = e.empty((self.cin, kd), torch.bfloat16) if self.need_dgrad else None
+            self.wd_lo = e.empty((self.cin, kd), torch.bfloat16) if self.need_dgrad else None
+        st = stream_ptr()
+        lib.pack_conv_weight(self.kernel.value, self.wf, self.wd, BF16, self.R, self.S, self.cin, self.cs, self.cout, Kp, st)
+        lib.pack_conv_weight_lo(self.kernel.value, self.wf_lo, self.wd_lo, self.R, self.S, self.cin, self.cs, self.cout, Kp, st)
+
+    @staticmethod
+    def _split(e, t):
+        hi = e.empty(t.shape, torch.bfloat16); lo = e.empty(t.shape, torch.bfloat16)
+        lib.split_bf16x2(t, hi, lo, t.numel(), stream_ptr())
+        return hi, lo
 
     def _timed(self, e, kind, x_shape, fn):
         """Optional per-launch CUDA-event timing (bench.py roofline pass)."""
@@ -158,6 +191,17 @@ class ConvOp:
             self._pack(e)
             self._timed(e, 'fprop', x.shape, lambda: lib.conv2d_fprop_tc(
                 x, self.wf, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs, self.cout, self.R, self.S, s, bn_sums, st))
+        elif e.conv_engine == 'tc3':
+            assert x.dtype == torch.float32 and y.dtype == torch.float32, 'BF16x3 is the fp32-storage mode'
+            self._pack3(e)
+            xs = self._split(e, x)
+            self._timed(e, 'fprop', x.shape, lambda: lib.conv2d_fprop_tc3(
+                xs[0], xs[1], self.wf, self.wf_lo, y, N, H, W, Cs, self.cout, self.R, self.S, s, st))
+            if bn_sums is not None:
+                lib.bn_stats(y, e.code(y.dtype), y.numel() // self.cout, self.cout, bn_sums, st)
+            if training:
+                self.saved_x = (x, xs)
+            return y
         else:
             lib.conv2d_fprop_simt(x, self.kernel.value, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs,
                                   self.cin, self.cout, self.R, self.S, s, st)
@@ -171,13 +215,17 @@ class ConvOp:
         e = get_engine()
         x = self.saved_x
         self.saved_x = None
+        if e.conv_engine == 'tc3':
+            return self._backward_tc3(e, x, dy, need_dx, dx_dtype)
         N, H, W, Cs = x.shape
         st = stream_ptr()
         assert dy.dtype == x.dtype, (dy.dtype, x.dtype)
         tc = e.conv_engine == 'tc'
         # fp32 storage (verification mode): the tcgen05 wgrad kernel is bf16-only (MN-major tf32 needs a
         # different swizzle atom), so the fp32 wgrad runs on the CUDA-core engine.
-        if tc and x.dtype == torch.bfloat16:
+        # The tcgen05 wgrad also needs 16-byte rows of dY (Cout % 8 == 0 in bf16): an odd-width supervised head
+        # (e.g. 10 classes) takes the CUDA-core kernel for that one small GEMM.
+        if tc and x.dtype == torch.bfloat16 and self.cout % 8 == 0:
             self._timed(e, 'wgrad', x.shape, lambda: lib.conv2d_wgrad_tc(
                 x, dy, self.kernel.grad, e.code(x.dtype), N, H, W, Cs, self.cin, self.cout, self.R, self.S,
                 self.stride, st))
@@ -195,6 +243,32 @@ class ConvOp:
             lib.conv2d_dgrad_simt(dy, self.kernel.value, dx, e.code(dy.dtype), e.code(dx.dtype), N, H, W,
                                   self.cin, self.cout, self.R, self.S, self.stride, st)
         return dx
+
+
+def _convop_backward_tc3(self, e, saved, dy, need_dx, dx_dtype):
+    x, (xh, xl) = saved
+    N, H, W, Cs = x.shape
+    st = stream_ptr()
+    assert dy.dtype == torch.float32
+    if self.cout % 8 == 0:
+        dh, dl = self._split(e, dy)
+        self._timed(e, 'wgrad', x.shape, lambda: lib.conv2d_wgrad_tc3(
+            xh, xl, dh, dl, self.kernel.grad, N, H, W, Cs, self.cin, self.cout, self.R, self.S, self.stride, st))
+    else:       # odd-width supervised head: 16-byte rows of dY are a tcgen05 wgrad requirement
+        dh = dl = None
+        lib.conv2d_wgrad_simt(x, dy, self.kernel.grad, F32, N, H, W, Cs, self.cin, self.cout, self.R, self.S,
+                              self.stride, st)
+    if not (need_dx and self.need_dgrad):
+        return None
+    if dh is None:
+        dh, dl = self._split(e, dy)
+    dx = e.empty((N, H, W, self.cin), torch.float32)
+    self._timed(e, 'dgrad', x.shape, lambda: lib.conv2d_dgrad_tc3(
+        dh, dl, self.wd, self.wd_lo, dx, N, H, W, self.cin, self.cout, self.R, self.S, self.stride, st))
+    return dx
+
+
+ConvOp._backward_tc3 = _convop_backward_tc3
 
 
 def conv_bn(conv, bn, x, training, **bn_kwargs):

@@ -44,6 +44,16 @@ class Trainer:
         Loss = contrastive + supervised + weight decay, divided by the number of
         replicas (tf2/run.py:587-617); gradients are summed across replicas
         (Keras `apply_gradients`, C3) and LARS is applied."""
+        loss = self.forward_backward(features, labels)
+        self.reduce_gradients()
+        self.optimizer.apply_gradients([(v.grad, v) for v in self.model.trainable_variables])
+        return loss
+
+    def forward_backward(self, features, labels):
+        """Forward, losses and the explicit backward pass: fills `.grad` of every trainable
+        variable with THIS replica's contribution.  The collectives inside (SyncBN statistics,
+        embedding / log-sum-exp all-gathers) are our own peer-memory kernels when
+        `strategy.comm` is set, so this part is CUDA-graph capturable at any replica count."""
         e, model, R = self.engine, self.model, self.strategy.num_replicas_in_sync
         st = stream_ptr()
         projection_head_outputs, supervised_head_outputs = model(features, training=True)
@@ -74,17 +84,31 @@ class Trainer:
             for v in model.trainable_variables:
                 if 'head_supervised' in v.name and 'bias' not in v.name:
                     lib.axpy(float(FLAGS.weight_decay) / R, v.value, v.grad, v.numel, st)
-        if R > 1:
-            self.strategy.all_reduce_sum(model.vs.flat_grad)          # C3: one flat buffer
-        self.optimizer.apply_gradients([(v.grad, v) for v in model.trainable_variables])
         return loss
 
+    def reduce_gradients(self):
+        """C3: cross-replica SUM of the gradients, one NCCL all-reduce over the flat buffer."""
+        if self.strategy.num_replicas_in_sync > 1:
+            self.strategy.all_reduce_sum(self.model.vs.flat_grad)
+
     # ------------------------------------------------------------------
-    def capture(self, features, labels, warmup=2):
+    def capture(self, features, labels, warmup=2, restore=False):
         """Captures `single_step` in a CUDA graph (the reference runs its steps inside
         one `tf.while_loop`, tf2/run.py:626-638).  `features`/`labels` become the
-        static input buffers: copy new data into them before `replay()`."""
+        static input buffers: copy new data into them before `replay()`.
+
+        The `warmup` eager steps run on a side stream first (lazy initialisation, allocator
+        warm-up) and are REAL steps: they update weights, momentum, moving statistics and
+        advance `optimizer.iterations`.  `restore=True` snapshots that state before the
+        warm-up and puts it back after the capture, so the first `replay()` is step
+        `optimizer.iterations` of the schedule on the pre-capture weights.  The capture
+        itself executes nothing and does not advance the schedule."""
         self._static = (features, labels)
+        opt, vs = self.optimizer, self.model.vs
+        opt.ensure_built(self.model.trainable_variables)      # H2D table copies must not land in the capture
+        snap = None
+        if restore:
+            snap = (vs.flat_value.clone(), vs.flat_moving.clone(), opt._flat_v.clone(), opt.iterations)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -92,15 +116,36 @@ class Trainer:
                 self.single_step(features, labels)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
         self.optimizer.stage_learning_rate()
-        with torch.cuda.graph(self._graph):
-            self._graph_loss = self.single_step(features, labels)
+        R = self.strategy.num_replicas_in_sync
+        if R == 1:
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._graph_loss = self.single_step(features, labels)
+            self._graph_apply = None
+        else:
+            # More than one replica: the in-step collectives are peer-memory kernels (capturable); the
+            # gradient all-reduce is NCCL and stays between two graphs.
+            if self.strategy.comm is None:
+                raise RuntimeError('CUDA-graph capture with %d replicas needs the peer-memory collectives '
+                                   '(strategy.comm); run eagerly instead' % R)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._graph_loss = self.forward_backward(features, labels)
+            self._graph_apply = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_apply):
+                self.optimizer.apply_gradients([(v.grad, v) for v in self.model.trainable_variables])
+        if snap is not None:
+            vs.flat_value.copy_(snap[0]); vs.flat_moving.copy_(snap[1]); opt._flat_v.copy_(snap[2])
+            opt.iterations = snap[3]
         return self._graph
 
     def replay(self):
         self.optimizer.prepare_replay()
         self._graph.replay()
+        if self._graph_apply is not None:
+            self.reduce_gradients()
+            self._graph_apply.replay()
         return self._graph_loss
 
 

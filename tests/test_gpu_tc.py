@@ -165,3 +165,52 @@ def test_tc_matches_simt_large(shape):
     assert rel_err(y_tc, y_ref) < 2e-4
     assert rel_err(dx_tc, dx_ref) < 2e-4
     assert rel_err(dw_tc, dw_ref) < 5e-4
+
+
+def _split(t):
+    from simclr_b200._lib import lib, stream_ptr
+    t = t.float().cuda().contiguous()
+    hi = torch.empty(t.shape, dtype=torch.bfloat16, device='cuda'); lo = torch.empty_like(hi)
+    lib.split_bf16x2(t, hi, lo, t.numel(), stream_ptr())
+    return hi, lo
+
+
+@pytest.mark.parametrize('case', [CASES[i] for i in (0, 1, 2, 4, 5, 6, 8, 12, 13, 16)])
+def test_tc3_bf16x3_fp32_accuracy(case):
+    """BF16x3 (fp32 operands split hi + lo, three tcgen05 GEMMs summed in fp32): fprop, dgrad and wgrad
+    against the fp64 oracle conv on UNROUNDED fp32 inputs at 2e-5 -- two orders below a single bf16 pass
+    (4e-3) and at the level of an fp32 CUDA-core conv."""
+    from simclr_b200._lib import lib, stream_ptr
+    N, H, W, Cin, Cs, Cout, k, s = case
+    x, w, xs = _mk(case, torch.float32, 11)
+    xo = x.double().requires_grad_(True); wo = w.double().requires_grad_(True)
+    yo = conv_reference(xo, wo, k, s)
+    dy = torch.randn(yo.shape)
+    yo.backward(dy.double())
+    xh, xl = _split(xs)
+    assert rel_err(xh.float() + xl.float(), xs) < 1e-5          # hi + lo carries 16 mantissa bits
+    K = k * (k + 1 if Cs == 4 else k) * Cs
+    Kp = (K + 63) // 64 * 64
+    kd = (k * k * Cout + 63) // 64 * 64
+    wf = torch.empty(Cout, Kp, dtype=torch.bfloat16, device='cuda'); wfl = torch.empty_like(wf)
+    has_wd = Cs == Cin
+    wd = torch.empty(Cin, kd, dtype=torch.bfloat16, device='cuda') if has_wd else None
+    wdl = torch.empty_like(wd) if has_wd else None
+    wc = w.float().cuda().contiguous()
+    lib.pack_conv_weight(wc, wf, wd, 1, k, k, Cin, Cs, Cout, Kp, stream_ptr())
+    lib.pack_conv_weight_lo(wc, wfl, wdl, k, k, Cin, Cs, Cout, Kp, stream_ptr())
+    y = torch.full(yo.shape, float('nan'), dtype=torch.float32, device='cuda')
+    lib.conv2d_fprop_tc3(xh, xl, wf, wfl, y, N, H, W, Cs, Cout, k, k, s, stream_ptr())
+    torch.cuda.synchronize()
+    assert rel_err(y, yo) < 2e-5
+    dh, dl = _split(dy)
+    if Cout % 8 == 0:
+        dw = torch.full((k, k, Cin, Cout), float('nan'), dtype=torch.float32, device='cuda')
+        lib.conv2d_wgrad_tc3(xh, xl, dh, dl, dw, N, H, W, Cs, Cin, Cout, k, k, s, stream_ptr())
+        torch.cuda.synchronize()
+        assert rel_err(dw, wo.grad) < 2e-5
+    if has_wd:
+        dx = torch.full((N, H, W, Cin), float('nan'), dtype=torch.float32, device='cuda')
+        lib.conv2d_dgrad_tc3(dh, dl, wd, wdl, dx, N, H, W, Cin, Cout, k, k, s, stream_ptr())
+        torch.cuda.synchronize()
+        assert rel_err(dx, xo.grad) < 2e-5
