@@ -23,7 +23,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GFLOP_PER_IMAGE = {(50, 1, 224): 48.574, (18, 1, 64): 1.751, (50, 2, 224): 192.406}
+# algorithmic conv GFLOP per image (2 views, fwd + dgrad + wgrad); key (depth, width, size, SK)
+GFLOP_PER_IMAGE = {(50, 1, 224, False): 48.574, (18, 1, 64, False): 1.751, (50, 2, 224, False): 192.406,
+                   (152, 2, 224, True): 841.196}
 
 
 def parse_args():
@@ -37,6 +39,13 @@ def parse_args():
     ap.add_argument('--width_multiplier', type=int, default=1)
     ap.add_argument('--image_size', type=int, default=224)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--engine', default='tc', choices=['tc', 'tc3', 'simt'],
+                    help='tc: bf16 tcgen05 (the benchmarked mode); tc3: fp32-accurate split-bf16 tcgen05 (needs --precision fp32)')
+    ap.add_argument('--sk_ratio', type=float, default=0.0, help='config 5: 0.0625')
+    ap.add_argument('--num_proj_layers', type=int, default=3)
+    ap.add_argument('--learning_rate', type=float, default=0.3)
+    ap.add_argument('--learning_rate_scaling', default='linear', choices=['linear', 'sqrt'])
+    ap.add_argument('--no_secondary', action='store_true', help='skip the fp32-accurate tensor-core mode measurement')
     ap.add_argument('--no_graph', action='store_true')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--cpu_batch', type=int, default=16)
@@ -45,9 +54,10 @@ def parse_args():
 
 
 def workload_string(args, world):
-    return ('ResNet-%d %dx, batch %d per GPU (global %d), %dx%d synthetic, proj_dim 128, temperature 0.1, LARS, '
-            'blur on, lineareval head on, global_bn on' % (args.resnet_depth, args.width_multiplier, args.batch,
-                                                           args.batch * world, args.image_size, args.image_size))
+    return ('ResNet-%d %dx%s, batch %d per GPU (global %d), %dx%d synthetic, proj_dim 128, %d-layer head, temperature 0.1, '
+            'LARS, blur on, lineareval head on, global_bn on'
+            % (args.resnet_depth, args.width_multiplier, ' SK' if args.sk_ratio > 0 else '', args.batch,
+               args.batch * world, args.image_size, args.image_size, args.num_proj_layers))
 
 
 def measured_peaks():
@@ -98,7 +108,8 @@ def oracle_step_time(args, batch, steps, warmup=1):
     import collections
     torch.set_num_threads(cpu_threads())
     cfg = default_cfg(resnet_depth=args.resnet_depth, width_multiplier=args.width_multiplier,
-                      image_size=args.image_size, train_batch_size=batch)
+                      image_size=args.image_size, train_batch_size=batch, sk_ratio=args.sk_ratio,
+                      num_proj_layers=args.num_proj_layers)
     m = OM.Model(cfg, 1000)
     P, S = m.init(0)
     V = collections.OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
@@ -172,8 +183,10 @@ def run_b200(args):
     B, S = args.batch, args.image_size
     flags_def.set_flags(resnet_depth=args.resnet_depth, width_multiplier=args.width_multiplier, image_size=S,
                         train_batch_size=B * world, temperature=0.1, proj_out_dim=128, optimizer='lars',
-                        use_tpu=False, b200_precision=args.precision, b200_conv_engine='tc')
-    eng = engine.set_engine(engine.Engine(precision=args.precision, conv_engine='tc'))
+                        sk_ratio=args.sk_ratio, num_proj_layers=args.num_proj_layers, learning_rate=args.learning_rate,
+                        learning_rate_scaling=args.learning_rate_scaling,
+                        use_tpu=False, b200_precision=args.precision, b200_conv_engine=args.engine)
+    eng = engine.set_engine(engine.Engine(precision=args.precision, conv_engine=args.engine))
     trainer = run.Trainer(num_classes=1000, num_examples=1281167, seed=0)
     features, labels = run.synthetic_batch(B, S, 1000, eng.device, 1234 + rank)
 
@@ -308,13 +321,14 @@ def run_b200(args):
         n_launch = max(len(eng.profile), 1)
         traffic = None; traffic_src = None
         tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic.json')
-        if os.path.exists(tj) and args.resnet_depth == 50 and args.width_multiplier == 1 and B == 512 and S == 224:
+        if os.path.exists(tj) and args.resnet_depth == 50 and args.width_multiplier == 1 and B == 512 and S == 224 \
+                and args.sk_ratio == 0 and args.engine == 'tc':
             try:
                 tr = json.load(open(tj))
                 traffic = tr['dram_bytes_per_launch']; traffic_src = 'profiles/traffic.json (%s)' % tr['source']
             except Exception:
                 traffic = None
-        key = (args.resnet_depth, args.width_multiplier, S)
+        key = (args.resnet_depth, args.width_multiplier, S, args.sk_ratio > 0)
         step_tflops = (ips / world) * GFLOP_PER_IMAGE[key] / 1e3 if key in GFLOP_PER_IMAGE else None
         roof = {'bound': 'tensor', 'kernel': 'igemm_kernel/wgrad_kernel (tcgen05 implicit GEMM, %d launches/step)' % sum(v[2] for v in by.values()),
                 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops'],
@@ -328,6 +342,41 @@ def run_b200(args):
 
     eng.profile = None
     log('profile pass done')
+    # ---- the fp32-accurate tensor-core mode (tc3: split-bf16 products, fp32 storage) beside the headline ----
+    # same network and image size on a smaller batch (its activations are fp32 and the headline graph keeps its
+    # own memory pool); eager launches, inputs resident, device-timed like `value`.
+    secondary = None
+    if world == 1 and args.engine == 'tc' and args.precision == 'bf16' and not args.no_secondary:
+        try:
+            free, _ = torch.cuda.mem_get_info()
+            b2 = min(64, B)
+            if free > 48 << 30:
+                flags_def.set_flags(train_batch_size=b2, b200_precision='fp32', b200_conv_engine='tc3')
+                eng2 = engine.set_engine(engine.Engine(precision='fp32', conv_engine='tc3'))
+                tr2 = run.Trainer(num_classes=1000, num_examples=1281167, seed=0)
+                f2, l2 = run.synthetic_batch(b2, S, 1000, eng2.device, 4321)
+                for _ in range(2):
+                    tr2.single_step(f2, l2)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                n2 = 3
+                for _ in range(n2):
+                    l2v = tr2.single_step(f2, l2)
+                b.record(); torch.cuda.synchronize()
+                ms2 = a.elapsed_time(b) / n2
+                secondary = {'engine': 'tc3 (three-way split-bf16 products on tcgen05, fp32 storage; 1e-3 step parity: '
+                                       'tests/test_gpu_step.py::test_step_parity_tc3)',
+                             'value': b2 / (ms2 / 1e3), 'unit': 'images/s', 'batch': b2, 'ms_per_step': ms2, 'steps': n2,
+                             'cuda_graph': False, 'loss': float(l2v)}
+                del tr2, f2, l2
+                engine.set_engine(eng)
+                flags_def.set_flags(train_batch_size=B * world, b200_precision=args.precision, b200_conv_engine=args.engine)
+            else:
+                secondary = {'skipped': 'only %.0f GiB free next to the headline graph' % (free / 2 ** 30)}
+        except Exception as ex:
+            secondary = {'failed': repr(ex)[:300]}
+        log('fp32-accurate tensor-core mode done')
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -342,7 +391,8 @@ def run_b200(args):
         line = {
             'metric': 'images/sec pretrain step', 'value': ips, 'unit': 'images/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'tf32',
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if args.precision == 'bf16' else ('f32 (split-bf16 tensor-core products)' if args.engine == 'tc3' else 'f32'),
             'data': 'synthetic',
             'config': {'workload': workload_string(args, world),
                        'l2': 'inputs larger than L2 (activations are GBs per step)',
@@ -352,6 +402,7 @@ def run_b200(args):
             'gpu_launches': launches_per_step * args.steps,
             'clocks': sampler.summary() if sampler else None,
             'roofline': roof, 'cpu_baseline': cpu, 'loss': loss_val,
+            'fp32_accurate_tensor_core_mode': secondary,
         }
         emit(line)
     if dist.is_initialized():

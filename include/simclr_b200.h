@@ -166,6 +166,16 @@ SIMCLR_API int simclr_bn_bwd_relu_reduce(const void* dz, int dtype, const void* 
  * sums_local (this replica's contribution, summed later with the other grads).
  * mask_scale / mask_shift (nullable, together): dz is masked on the fly with
  * [mask_scale*y + mask_shift > 0] (pairs with simclr_bn_bwd_relu_reduce). */
+/* Block tail (tf2/resnet.py:382,487: relu(bn(y) + shortcut)) with the ReLU mask kept as ONE BIT per element:
+ * `relu_mask_bits` [rows*C/8] bytes, bit k of byte i = [z > 0] of channel k of 16-byte vector i.  The backward
+ * reduction then reads 1/16 of the bytes it would read from z: dz <- (dz + dz2) * mask in place,
+ * sums [2][C] = (sum dz, sum dz*xhat), as simclr_bn_bwd_reduce. */
+SIMCLR_API int simclr_bn_apply_relu_mask(const void* y, int y_dtype, const void* residual, void* z, int z_dtype,
+                                         int64_t rows, int64_t C, const float* scale, const float* shift,
+                                         uint8_t* relu_mask_bits, void* stream);
+SIMCLR_API int simclr_bn_bwd_reduce_bits(void* dz, const void* dz2, const uint8_t* relu_mask_bits, int dtype,
+                                         const void* y, int y_dtype, int64_t rows, int64_t C, const float* mean,
+                                         const float* rstd, double* sums, void* stream);
 SIMCLR_API int simclr_bn_bwd_apply(const void* dz, int dtype, const void* y, int y_dtype, void* dy,
                                    int dy_dtype, int64_t rows, int64_t C, const float* mean,
                                    const float* rstd, const float* gamma, const double* sums,
@@ -207,6 +217,16 @@ SIMCLR_API int simclr_global_avgpool_bwd(const void* dy, int dy_dtype, void* dx,
 SIMCLR_API int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, int64_t R,
                                        int64_t S, int64_t Cin, int64_t Cs, int64_t Cout, int64_t Kp,
                                        void* stream);
+/* Every layer's packed bf16 operands in ONE launch (the per-step refresh after the optimizer update):
+ * `table_dev` is a device array of n_layers rows of 10 int64 {w_hwio, wf, wd (0: none), R, S, Cin, Cs,
+ * Cout, Kp, Kdp}, same layouts as simclr_pack_conv_weight with dtype bf16. */
+SIMCLR_API int simclr_pack_conv_weights_multi(const void* table_dev, int64_t n_layers, void* stream);
+/* Accumulation outputs -- the BatchNorm sums of simclr_conv2d_fprop_tc / simclr_bn_stats /
+ * simclr_bn_bwd_*reduce and dW of simclr_conv2d_wgrad_tc -- are zeroed by the call that fills them.  A caller
+ * that keeps them in pooled buffers and zeroes those once per step (simclr_memset_zero) switches the per-call
+ * memsets off with on = 1; returns the previous setting.  Process-wide, not thread-safe. */
+SIMCLR_API int simclr_set_accumulate_prezeroed(int on);
+SIMCLR_API int simclr_memset_zero(void* p, int64_t bytes, void* stream);
 /* bn_sums (nullable): [2][Cout] doubles receiving sum y / sum y^2 of the stored outputs -- the
  * BatchNorm statistics of tf2/resnet.py:50-72 fused into the conv epilogue (zeroed by the call). */
 SIMCLR_API int simclr_conv2d_fprop_tc(const void* x, const void* wf, void* y, int dtype, int y_dtype,
@@ -220,24 +240,29 @@ SIMCLR_API int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, 
                                       int64_t H, int64_t W, int64_t Cs, int64_t Cin, int64_t Cout, int64_t R,
                                       int64_t S, int64_t stride, void* stream);
 
-/* BF16x3 -- the tensor-core VERIFICATION mode (fp32 storage, 1e-3 step parity with the fp32
- * reference of tf2/run.py:557-622 on the tcgen05 pipe).  Every fp32 operand v is split
- * hi = bf16(v), lo = bf16(v - hi) (`simclr_split_bf16x2`, `simclr_pack_conv_weight` for the hi part
- * and `simclr_pack_conv_weight_lo` for the residual part of the packed weights, same layouts) and a
- * product is taken as hi*hi + hi*lo + lo*hi: three exact-product / fp32-accumulate GEMMs summed in
- * fp32 (TMA reduce-add).  Outputs are fp32 and overwritten. */
-SIMCLR_API int simclr_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream);
-SIMCLR_API int simclr_pack_conv_weight_lo(const float* w_hwio, void* wf_lo, void* wd_lo, int64_t R, int64_t S,
-                                          int64_t Cin, int64_t Cs, int64_t Cout, int64_t Kp, void* stream);
-SIMCLR_API int simclr_conv2d_fprop_tc3(const void* x_hi, const void* x_lo, const void* wf_hi, const void* wf_lo,
-                                       float* y, int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cout,
-                                       int64_t R, int64_t S, int64_t stride, void* stream);
-SIMCLR_API int simclr_conv2d_dgrad_tc3(const void* dy_hi, const void* dy_lo, const void* wd_hi, const void* wd_lo,
-                                       float* dx, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
-                                       int64_t R, int64_t S, int64_t stride, void* stream);
-SIMCLR_API int simclr_conv2d_wgrad_tc3(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo,
-                                       float* dw, int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cin,
-                                       int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream);
+/* Split-bf16 products -- the tensor-core VERIFICATION mode (`--b200_conv_engine=tc3`: fp32 storage,
+ * 1e-3 step parity with the fp32 reference of tf2/run.py:557-622 on the tcgen05 pipe).  Every fp32
+ * operand v is split three ways, v = v0 + v1 + v2 with v0 = bf16(v), v1 = bf16(v - v0),
+ * v2 = bf16(v - v0 - v1) (`simclr_split_bf16x3`; `simclr_pack_conv_weight_part` writes part 0 / 1 / 2
+ * of the packed weights in the layouts of `simclr_pack_conv_weight`), and a product is taken as
+ * a0*b0 + a0*b1 + a1*b0 + a1*b1 + a0*b2 + a2*b0: six exact-product / fp32-accumulate GEMMs summed in
+ * fp32 (TMA reduce-add); the dropped terms are 2^-24 relative.  Outputs are fp32 and overwritten. */
+SIMCLR_API int simclr_split_bf16x3(const float* x, void* v0, void* v1, void* v2, int64_t n, void* stream);
+SIMCLR_API int simclr_pack_conv_weight_part(const float* w_hwio, void* wf, void* wd, int part, int64_t R,
+                                            int64_t S, int64_t Cin, int64_t Cs, int64_t Cout, int64_t Kp,
+                                            void* stream);
+SIMCLR_API int simclr_conv2d_fprop_tc3(const void* x0, const void* x1, const void* x2, const void* wf0,
+                                       const void* wf1, const void* wf2, float* y, int64_t N, int64_t H,
+                                       int64_t W, int64_t Cs, int64_t Cout, int64_t R, int64_t S,
+                                       int64_t stride, void* stream);
+SIMCLR_API int simclr_conv2d_dgrad_tc3(const void* dy0, const void* dy1, const void* dy2, const void* wd0,
+                                       const void* wd1, const void* wd2, float* dx, int64_t N, int64_t H,
+                                       int64_t W, int64_t Cin, int64_t Cout, int64_t R, int64_t S,
+                                       int64_t stride, void* stream);
+SIMCLR_API int simclr_conv2d_wgrad_tc3(const void* x0, const void* x1, const void* x2, const void* dy0,
+                                       const void* dy1, const void* dy2, float* dw, int64_t N, int64_t H,
+                                       int64_t W, int64_t Cs, int64_t Cin, int64_t Cout, int64_t R, int64_t S,
+                                       int64_t stride, void* stream);
 
 /* CUDA-core fp32 engine reading the fp32 HWIO master directly (verification
  * engine for the tcgen05 path; not the default). */

@@ -55,6 +55,8 @@ inline RedLayout red_layout(int64_t C) {
 // optional in-place dz <- (dz + dz2) * [z > 0].  mode 2: bwd reduce of a BN+ReLU
 // without residual: the mask [scale*y + shift > 0] is recomputed from y (a2 = scale,
 // zmask = shift, both fp32 [C]); dz is neither re-read from a mask tensor nor written.
+// mode 3: mode 1 with the ReLU mask of the block tail as ONE BIT per element (byte i = the 8 channels
+// of 16-byte vector i, written by bn_apply_kernel) instead of the output tensor z: 1/16 of the bytes.
 // The kernels are HBM-latency bound: each thread keeps 4 (modes 0, 2) or 2 (mode 1) rows of
 // 16-byte loads in flight, two 256-thread CTAs per SM.
 template <typename T, typename Ty, int MODE>
@@ -64,7 +66,8 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
                  const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ sums) {
   extern __shared__ double sh[];  // [row_lanes][P*8][2]
   const T* __restrict__ a2 = MODE == 2 ? nullptr : (const T*)a2_;
-  const T* __restrict__ zmask = MODE == 2 ? nullptr : (const T*)zmask_;
+  const T* __restrict__ zmask = (MODE == 2 || MODE == 3) ? nullptr : (const T*)zmask_;
+  const uint8_t* __restrict__ zbits = MODE == 3 ? (const uint8_t*)zmask_ : nullptr;
   const int tx = threadIdx.x % P, ty = threadIdx.x / P;
   const int row_lanes = BT / P;
   const int cvecs = C / 8;
@@ -148,7 +151,7 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
 #pragma unroll
         for (int i = 0; i < 8; ++i) mu[i] = mean[cv * 8 + i];
         const bool has2 = a2 != nullptr, hasz = zmask != nullptr;
-        auto acc = [&](int64_t off, const Raw8<T>& qv, const Raw8<T>& qw, const Raw8<T>& qz, const Raw8<Ty>& qy) {
+        auto acc = [&](int64_t off, const Raw8<T>& qv, const Raw8<T>& qw, const Raw8<T>& qz, const Raw8<Ty>& qy, unsigned bits) {
           float v[8], yy[8]; qv.to(v); qy.to(yy);
           if (has2) {
             float w[8]; qw.to(w);
@@ -160,7 +163,11 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = (z[i] > 0.f) ? v[i] : 0.f;
           }
-          if (has2 || hasz) {
+          if (MODE == 3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = ((bits >> i) & 1u) ? v[i] : 0.f;
+          }
+          if (has2 || hasz || MODE == 3) {
             store8<T>(a + off, v);
             // keep the sums consistent with what phase 2 will read back
             if (sizeof(T) == 2) {
@@ -173,16 +180,17 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
         };
         for (; r + row_lanes < r1; r += 2 * row_lanes) {
           const int64_t off = r * C + (int64_t)cv * 8;
-          Raw8<T> qv[2], qw[2], qz[2]; Raw8<Ty> qy[2];
+          Raw8<T> qv[2], qw[2], qz[2]; Raw8<Ty> qy[2]; unsigned qb[2] = {0u, 0u};
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             qv[u].ld(a + off + u * lane_step);
             if (has2) qw[u].ld(a2 + off + u * lane_step); else qw[u] = qv[u];
             if (hasz) qz[u].ld(zmask + off + u * lane_step); else qz[u] = qv[u];
+            if (MODE == 3) qb[u] = zbits[(off + u * lane_step) >> 3];
             qy[u].ld(y + off + u * lane_step);
           }
 #pragma unroll
-          for (int u = 0; u < 2; ++u) acc(off + u * lane_step, qv[u], qw[u], qz[u], qy[u]);
+          for (int u = 0; u < 2; ++u) acc(off + u * lane_step, qv[u], qw[u], qz[u], qy[u], qb[u]);
         }
         for (; r < r1; r += row_lanes) {
           const int64_t off = r * C + (int64_t)cv * 8;
@@ -190,8 +198,9 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           qv.ld(a + off);
           if (has2) qw.ld(a2 + off); else qw = qv;
           if (hasz) qz.ld(zmask + off); else qz = qv;
+          const unsigned qb = MODE == 3 ? (unsigned)zbits[off >> 3] : 0u;
           qy.ld(y + off);
-          acc(off, qv, qw, qz, qy);
+          acc(off, qv, qw, qz, qy, qb);
         }
         fold();
 #pragma unroll
@@ -254,7 +263,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 template <typename Ty, typename Tz>
 __global__ void __launch_bounds__(BT)
 bn_apply_kernel(const Ty* __restrict__ y, const Tz* __restrict__ res, Tz* __restrict__ z, int64_t nvec, int C,
-                const float* __restrict__ scale, const float* __restrict__ shift, int relu) {
+                const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                uint8_t* __restrict__ mask_bits) {
   const int64_t stride = (int64_t)gridDim.x * BT;
   int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
   const bool fixed_c = (stride * 8) % C == 0;
@@ -274,6 +284,12 @@ bn_apply_kernel(const Ty* __restrict__ y, const Tz* __restrict__ res, Tz* __rest
       for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
     }
     store8<Tz>(z + off, v);
+    if (mask_bits != nullptr) {          // [z > 0] of the stored (rounded) outputs, one bit per element
+      unsigned b = 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b |= (to_f<Tz>(from_f<Tz>(v[k])) > 0.f ? 1u : 0u) << k;
+      mask_bits[off >> 3] = (uint8_t)b;
+    }
   };
   if (fixed_c) {
     for (; i + stride < nvec; i += 2 * stride) {
@@ -384,8 +400,10 @@ int launch_reduce(void* a, const void* a2, const void* zmask, const void* y, int
   const int rows_per_block = (int)((rows + nblocks - 1) / nblocks);
   nblocks = (rows + rows_per_block - 1) / rows_per_block;
   const size_t smem = (size_t)BT * 16 * sizeof(double);
-  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st);
-  if (e != cudaSuccess) { set_error("bn reduce memset: %s", cudaGetErrorString(e)); return (int)e; }
+  if (!accumulate_prezeroed()) {
+    cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st);
+    if (e != cudaSuccess) { set_error("bn reduce memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
   bn_reduce_kernel<T, Ty, MODE><<<(unsigned)nblocks, BT, smem, st>>>(
       (T*)a, a2, zmask, (const Ty*)y, rows, (int)C, l.P, rows_per_block, mean, rstd, sums);
   SIMCLR_CHECK_LAUNCH();
@@ -422,8 +440,8 @@ int simclr_bn_finalize(const double* sums, double count, const float* gamma, con
   return SIMCLR_OK;
 }
 
-int simclr_bn_apply(const void* y, int y_dtype, const void* residual, void* z, int z_dtype, int64_t rows,
-                    int64_t C, const float* scale, const float* shift, int relu, void* stream) {
+static int bn_apply_impl(const void* y, int y_dtype, const void* residual, void* z, int z_dtype, int64_t rows,
+                         int64_t C, const float* scale, const float* shift, int relu, uint8_t* mask_bits, void* stream) {
   SIMCLR_CHECK_ARG(y && z && scale && shift, "bn_apply: null pointer");
   SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_apply: need rows>0 and C%%8==0");
   SIMCLR_CHECK_ARG(aligned16(y) && aligned16(z) && aligned16(residual), "bn_apply: pointers must be 16-byte aligned");
@@ -431,16 +449,47 @@ int simclr_bn_apply(const void* y, int y_dtype, const void* residual, void* z, i
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = ew_grid_c(nvec, C);
   if (y_dtype == SIMCLR_F32 && z_dtype == SIMCLR_F32)
-    bn_apply_kernel<float, float><<<grid, BT, 0, st>>>((const float*)y, (const float*)residual, (float*)z, nvec, (int)C, scale, shift, relu);
+    bn_apply_kernel<float, float><<<grid, BT, 0, st>>>((const float*)y, (const float*)residual, (float*)z, nvec, (int)C, scale, shift, relu, mask_bits);
   else if (y_dtype == SIMCLR_BF16 && z_dtype == SIMCLR_BF16)
-    bn_apply_kernel<bf16, bf16><<<grid, BT, 0, st>>>((const bf16*)y, (const bf16*)residual, (bf16*)z, nvec, (int)C, scale, shift, relu);
+    bn_apply_kernel<bf16, bf16><<<grid, BT, 0, st>>>((const bf16*)y, (const bf16*)residual, (bf16*)z, nvec, (int)C, scale, shift, relu, mask_bits);
   else if (y_dtype == SIMCLR_F32 && z_dtype == SIMCLR_BF16)
-    bn_apply_kernel<float, bf16><<<grid, BT, 0, st>>>((const float*)y, (const bf16*)residual, (bf16*)z, nvec, (int)C, scale, shift, relu);
+    bn_apply_kernel<float, bf16><<<grid, BT, 0, st>>>((const float*)y, (const bf16*)residual, (bf16*)z, nvec, (int)C, scale, shift, relu, mask_bits);
   else if (y_dtype == SIMCLR_BF16 && z_dtype == SIMCLR_F32)
-    bn_apply_kernel<bf16, float><<<grid, BT, 0, st>>>((const bf16*)y, (const float*)residual, (float*)z, nvec, (int)C, scale, shift, relu);
+    bn_apply_kernel<bf16, float><<<grid, BT, 0, st>>>((const bf16*)y, (const float*)residual, (float*)z, nvec, (int)C, scale, shift, relu, mask_bits);
   else { set_error("bn_apply: unknown dtypes %d/%d", y_dtype, z_dtype); return SIMCLR_ERR_INVALID_ARG; }
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
+}
+
+int simclr_bn_apply(const void* y, int y_dtype, const void* residual, void* z, int z_dtype, int64_t rows,
+                    int64_t C, const float* scale, const float* shift, int relu, void* stream) {
+  return bn_apply_impl(y, y_dtype, residual, z, z_dtype, rows, C, scale, shift, relu, nullptr, stream);
+}
+
+int simclr_bn_apply_relu_mask(const void* y, int y_dtype, const void* residual, void* z, int z_dtype, int64_t rows,
+                              int64_t C, const float* scale, const float* shift, uint8_t* relu_mask_bits,
+                              void* stream) {
+  SIMCLR_CHECK_ARG(relu_mask_bits, "bn_apply_relu_mask: null mask");
+  return bn_apply_impl(y, y_dtype, residual, z, z_dtype, rows, C, scale, shift, 1, relu_mask_bits, stream);
+}
+
+int simclr_bn_bwd_reduce_bits(void* dz, const void* dz2, const uint8_t* relu_mask_bits, int dtype, const void* y,
+                              int y_dtype, int64_t rows, int64_t C, const float* mean, const float* rstd,
+                              double* sums, void* stream) {
+  SIMCLR_CHECK_ARG(dz && relu_mask_bits && y && mean && rstd && sums, "bn_bwd_reduce_bits: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_bwd_reduce_bits: need rows>0 and C%%8==0");
+  SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(dz2) && aligned16(y), "bn_bwd_reduce_bits: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SIMCLR_F32 && y_dtype == SIMCLR_F32)
+    return launch_reduce<float, float, 3>(dz, dz2, relu_mask_bits, y, rows, C, mean, rstd, sums, st);
+  if (dtype == SIMCLR_BF16 && y_dtype == SIMCLR_BF16)
+    return launch_reduce<bf16, bf16, 3>(dz, dz2, relu_mask_bits, y, rows, C, mean, rstd, sums, st);
+  if (dtype == SIMCLR_BF16 && y_dtype == SIMCLR_F32)
+    return launch_reduce<bf16, float, 3>(dz, dz2, relu_mask_bits, y, rows, C, mean, rstd, sums, st);
+  if (dtype == SIMCLR_F32 && y_dtype == SIMCLR_BF16)
+    return launch_reduce<float, bf16, 3>(dz, dz2, relu_mask_bits, y, rows, C, mean, rstd, sums, st);
+  set_error("bn_bwd_reduce_bits: unknown dtypes");
+  return SIMCLR_ERR_INVALID_ARG;
 }
 
 int simclr_bn_bwd_reduce(void* dz, const void* dz2, const void* relu_mask_z, int dtype, const void* y,

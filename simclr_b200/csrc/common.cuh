@@ -12,6 +12,8 @@ namespace simclr {
 
 // ---- error reporting (thread-local text) ---------------------
 void set_error(const char* fmt, ...);
+// true: the caller has zeroed the accumulation outputs (BN sums, dW) itself (simclr_set_accumulate_prezeroed)
+bool accumulate_prezeroed();
 
 #define SIMCLR_CHECK_ARG(cond, ...)                                   \
   do {                                                                \

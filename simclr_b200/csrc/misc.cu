@@ -5,6 +5,12 @@
 
 namespace simclr {
 
+// Accumulation outputs (BN statistic sums, dW of the tcgen05 wgrad) are normally zeroed by the call that
+// fills them -- one cudaMemsetAsync per call, ~170 per ResNet-50 step.  A caller that zeroes them itself (one
+// memset per step over pooled buffers) switches that off with simclr_set_accumulate_prezeroed(1).
+static bool g_prezeroed = false;
+bool accumulate_prezeroed() { return g_prezeroed; }
+
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt);
@@ -115,20 +121,55 @@ __global__ void add_inplace_kernel(T* __restrict__ a, const T* __restrict__ b, i
 // wd [Cin][Kdp] (k=(r*S+s)*Cout+co, zero padded to the K block).
 // bf16 with 4 stored channels (the stem): k = (r*(S+1) + s+1)*4 + c, slot s' = 0 of every filter
 // row zero -- S+1 slots make a filter row a whole number of 16-byte pixel pairs.
-// PART 0: the value itself; PART 1 (bf16 only): the residual v - bf16(v) of the BF16x3 split
+// Three-way bf16 split of an fp32 value: v = a + b + c exactly up to 2^-25 |v| (8 + 8 + 8 mantissa bits),
+// a = bf16(v), b = bf16(v - a), c = bf16(v - a - b).  PART selects the term (0: the value itself).
 template <typename T, int PART> __device__ __forceinline__ T pack_part(float v) {
   if (PART == 0) return from_f<T>(v);
-  return from_f<T>(v - __bfloat162float(__float2bfloat16_rn(v)));
+  const float r1 = v - __bfloat162float(__float2bfloat16_rn(v));
+  if (PART == 1) return from_f<T>(r1);
+  return from_f<T>(r1 - __bfloat162float(__float2bfloat16_rn(r1)));
 }
 
-// x fp32 -> hi = bf16(x), lo = bf16(x - hi): x = hi + lo up to 2^-17 |x| (BF16x3 operands)
-__global__ void split_bf16x2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo, int64_t n) {
+__global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a,
+                                    __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ c, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i];
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi[i] = h;
-    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    a[i] = h; b[i] = m;
+    c[i] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+  }
+}
+
+// All conv / dense layers in one launch: blockIdx.y selects the layer (table row of 10 int64:
+// w, wf, wd, R, S, Cin, Cs, Cout, Kp, Kdp), blockIdx.x strides over its elements.
+__global__ void pack_weights_multi_kernel(const long long* __restrict__ table) {
+  const long long* t = table + (long long)blockIdx.y * 10;
+  const float* __restrict__ w = reinterpret_cast<const float*>(t[0]);
+  __nv_bfloat16* __restrict__ wf = reinterpret_cast<__nv_bfloat16*>(t[1]);
+  __nv_bfloat16* __restrict__ wd = reinterpret_cast<__nv_bfloat16*>(t[2]);
+  const int R = (int)t[3], S = (int)t[4], Cin = (int)t[5], Cs = (int)t[6], Cout = (int)t[7], Kp = (int)t[8], Kdp = (int)t[9];
+  const int64_t nf = (int64_t)Cout * Kp;
+  const int64_t nd = wd ? (int64_t)Cin * Kdp : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < nf) {
+      const int co = (int)(i / Kp), k = (int)(i % Kp);
+      const int tap = k / Cs, c = k % Cs;
+      float v = 0.f;
+      if (Cs == 4) {
+        const int r = tap / (S + 1), sp = tap % (S + 1);
+        if (r < R && sp >= 1 && c < Cin) v = w[((int64_t)(r * S + sp - 1) * Cin + c) * Cout + co];
+      } else if (tap < R * S && c < Cin) {
+        v = w[((int64_t)tap * Cin + c) * Cout + co];
+      }
+      wf[i] = __float2bfloat16_rn(v);
+    } else {
+      const int64_t j = i - nf;
+      const int ci = (int)(j / Kdp), k = (int)(j % Kdp);
+      const int tap = k / Cout, co = k % Cout;
+      wd[j] = __float2bfloat16_rn(tap < R * S ? w[((int64_t)tap * Cin + ci) * Cout + co] : 0.f);
+    }
   }
 }
 
@@ -396,22 +437,44 @@ int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, 
   return SIMCLR_OK;
 }
 
-int simclr_pack_conv_weight_lo(const float* w_hwio, void* wf_lo, void* wd_lo, int64_t R, int64_t S, int64_t Cin,
-                               int64_t Cs, int64_t Cout, int64_t Kp, void* stream) {
-  SIMCLR_CHECK_ARG(w_hwio && wf_lo, "pack_conv_weight_lo: null pointer");
-  SIMCLR_CHECK_ARG(R > 0 && S > 0 && Cin > 0 && Cs >= Cin && Cout > 0 && Kp % 64 == 0, "pack_conv_weight_lo: bad shape");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t Kdp = (R * S * Cout + 63) / 64 * 64;
-  const int64_t total = Cout * Kp + (wd_lo ? Cin * Kdp : 0);
-  pack_weight_kernel<bf16, 1><<<grid_for(total, 256), 256, 0, st>>>(w_hwio, (bf16*)wf_lo, (bf16*)wd_lo, (int)R, (int)S,
-                                                                     (int)Cin, (int)Cs, (int)Cout, (int)Kp, (int)Kdp);
+int simclr_pack_conv_weights_multi(const void* table_dev, int64_t n_layers, void* stream) {
+  SIMCLR_CHECK_ARG(table_dev && n_layers > 0 && n_layers < 65536, "pack_conv_weights_multi: bad arguments");
+  pack_weights_multi_kernel<<<dim3(48, (unsigned)n_layers), 256, 0, (cudaStream_t)stream>>>((const long long*)table_dev);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
 
-int simclr_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream) {
-  SIMCLR_CHECK_ARG(x && hi && lo && n > 0, "split_bf16x2: bad arguments");
-  split_bf16x2_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)hi, (bf16*)lo, n);
+int simclr_set_accumulate_prezeroed(int on) {
+  const int prev = simclr::g_prezeroed ? 1 : 0;
+  simclr::g_prezeroed = on != 0;
+  return prev;
+}
+
+int simclr_memset_zero(void* p, int64_t bytes, void* stream) {
+  SIMCLR_CHECK_ARG(p && bytes > 0, "memset_zero: bad arguments");
+  SIMCLR_CHECK_CUDA(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
+  return SIMCLR_OK;
+}
+
+int simclr_pack_conv_weight_part(const float* w_hwio, void* wf, void* wd, int part, int64_t R, int64_t S, int64_t Cin,
+                                 int64_t Cs, int64_t Cout, int64_t Kp, void* stream) {
+  SIMCLR_CHECK_ARG(w_hwio && wf, "pack_conv_weight_part: null pointer");
+  SIMCLR_CHECK_ARG(part >= 0 && part <= 2, "pack_conv_weight_part: part must be 0, 1 or 2");
+  SIMCLR_CHECK_ARG(R > 0 && S > 0 && Cin > 0 && Cs >= Cin && Cout > 0 && Kp % 64 == 0, "pack_conv_weight_part: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t Kdp = (R * S * Cout + 63) / 64 * 64;
+  const int64_t total = Cout * Kp + (wd ? Cin * Kdp : 0);
+  const unsigned grid = grid_for(total, 256);
+#define PACK(P) pack_weight_kernel<bf16, P><<<grid, 256, 0, st>>>(w_hwio, (bf16*)wf, (bf16*)wd, (int)R, (int)S, (int)Cin, (int)Cs, (int)Cout, (int)Kp, (int)Kdp)
+  if (part == 0) PACK(0); else if (part == 1) PACK(1); else PACK(2);
+#undef PACK
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_split_bf16x3(const float* x, void* a, void* b, void* c, int64_t n, void* stream) {
+  SIMCLR_CHECK_ARG(x && a && b && c && n > 0, "split_bf16x3: bad arguments");
+  split_bf16x3_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)a, (bf16*)b, (bf16*)c, n);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }

@@ -317,5 +317,11 @@ inline int make_tmap_im2col(CUtensorMap* map, const void* base, int elt_bytes, u
   return SIMCLR_OK;
 }
 
+// 3x3 stride-1 fprop / dgrad with halo reuse (tc_halo.cu); see run_halo3x3 for the argument meaning
+bool halo3x3_applicable(int dtype, int out_dtype, int64_t N, int64_t H, int64_t W, int64_t C, int64_t n_out, int64_t R,
+                        int64_t S, int64_t stride, const void* src, const void* wk, const void* out);
+int run_halo3x3(int mode, const void* src, const void* wk, void* out, int64_t N, int64_t H, int64_t W, int64_t C,
+                int64_t n_out, cudaStream_t st, double* bn_sums);
+
 }  // namespace tc
 }  // namespace simclr

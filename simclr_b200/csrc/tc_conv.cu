@@ -59,7 +59,7 @@ struct Geom {
   // TMA im2col feed of the gathered operand: base pixel of GEMM row (n, p, q) is
   // (q*stride + im_base, p*stride + im_base); the tap goes into the instruction's filter offsets
   int im2col, im_base, im_nimg;
-  int accum;           // fp32 outputs only: add into `out` (TMA reduce-add / atomics) instead of storing (BF16x3 passes)
+  int accum;           // fp32 outputs only: add into `out` (TMA reduce-add / atomics) instead of storing (tc3 passes)
 };
 
 template <typename T> struct Elt;
@@ -963,6 +963,9 @@ int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, i
   if (!aligned16(src) || !aligned16(wk)) { set_error("%s: operands must be 16-byte aligned", what); return SIMCLR_ERR_INVALID_ARG; }
   const int64_t M = N * P * Q;
   if (M >= (1ll << 31)) { set_error("%s: M too large", what); return SIMCLR_ERR_UNSUPPORTED; }
+  // 64 / 128-channel 3x3 stride-1 layers: halo-reuse kernel (one slab load instead of nine im2col loads)
+  if (!accum && P == Hs && Q == Ws && halo3x3_applicable(dtype, out_dtype, N, Hs, Ws, Cs, n_out, R, S, stride, src, wk, out))
+    return run_halo3x3(mode, src, wk, out, N, Hs, Ws, Cs, n_out, st, bn_sums);
   // Stem (4 stored channels, bf16): K runs over (r, s' in [0, S], c) with a zero slot s' = 0, i.e. the
   // filter is S+1 wide with one more pixel of left padding.  With stride 2, odd padding and an even
   // width the S+1 slots are whole 16-byte pixel pairs: the tensor is then read as [N][H][W/2][8] with
@@ -1011,8 +1014,10 @@ int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, i
   else tout = tb;
   if (bn_sums) {
     if (!tma_epi) { set_error("%s: fused BN statistics need 16-byte aligned output rows", what); return SIMCLR_ERR_UNSUPPORTED; }
-    cudaError_t e = cudaMemsetAsync(bn_sums, 0, 2 * (size_t)n_out * sizeof(double), st);
-    if (e != cudaSuccess) { set_error("%s: memset: %s", what, cudaGetErrorString(e)); return (int)e; }
+    if (!accumulate_prezeroed()) {
+      cudaError_t e = cudaMemsetAsync(bn_sums, 0, 2 * (size_t)n_out * sizeof(double), st);
+      if (e != cudaSuccess) { set_error("%s: memset: %s", what, cudaGetErrorString(e)); return (int)e; }
+    }
   }
   if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_BF16) return dispatch_igemm<__nv_bfloat16, __nv_bfloat16>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st, bn_sums);
   if (dtype == SIMCLR_BF16 && out_dtype == SIMCLR_F32) return dispatch_igemm<__nv_bfloat16, float>(bn, a_tma, smallc, tma_epi, ta, tb, tout, g, st, bn_sums);
@@ -1249,7 +1254,7 @@ static int wgrad_tc_impl(const void* x, const void* dy, float* dw, int dtype, in
   const bool tma_red = !stem && Cs == Cin && aligned16(dw) && (Cout * 4) % 16 == 0;
   if (tma_red) { rc = make_tmap_2d(&tdw, dw, 4, (uint64_t)(R * S * Cin), (uint64_t)Cout, (uint64_t)Cout * 4, 128, 32); if (rc) return rc; }
   else tdw = tdy;
-  if (zero) SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(R * S * Cin * Cout) * sizeof(float), st));
+  if (zero && !accumulate_prezeroed()) SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(R * S * Cin * Cout) * sizeof(float), st));
   if (dtype == SIMCLR_BF16) return dispatch_wgrad<__nv_bfloat16>(bn, smallc, a_tma, tma_red, tx, tdy, tdw, g, dw, st);
   set_error("conv2d_wgrad_tc: unknown dtype %d", dtype);
   return SIMCLR_ERR_INVALID_ARG;
@@ -1261,49 +1266,54 @@ int simclr_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, int dtype, 
 }
 
 // ---------------------------------------------------------------------------
-// BF16x3: fp32-accurate products on the bf16 tensor pipe.  Every fp32 operand is split as
-// v = hi + lo (+ 2^-17 |v|), hi = bf16(v), lo = bf16(v - hi); a product a*b is taken as
-// a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (the dropped lo*lo term is 2^-16 relative), each of the three
-// an exact-product / fp32-accumulate tcgen05 GEMM, summed in fp32 at L2 (TMA reduce-add).  This
-// is the tensor-core verification mode: fp32 storage, 1e-3 step parity with the fp32 reference.
+// Split-bf16 products: fp32-accurate GEMMs on the bf16 tensor pipe.  Every fp32 operand is split three
+// ways, v = v0 + v1 + v2 (8 + 8 + 8 mantissa bits, exact to 2^-25 |v|), and a product a*b is taken as
+//   a0*b0 + (a0*b1 + a1*b0) + (a1*b1 + a0*b2 + a2*b0)
+// -- all terms down to 2^-16 relative; what is dropped is 2^-24 -- each an exact-product / fp32-accumulate
+// tcgen05 GEMM, summed in fp32 at L2 (TMA reduce-add).  A two-way split (three GEMMs) leaves 2^-17 per
+// operand: measured 1e-2 on the step's gradients, not enough for the 1e-3 bar.  This is the tensor-core
+// verification mode: fp32 storage, 1e-3 step parity with the fp32 reference.
 // ---------------------------------------------------------------------------
-int simclr_conv2d_fprop_tc3(const void* x_hi, const void* x_lo, const void* wf_hi, const void* wf_lo, float* y,
-                            int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cout, int64_t R, int64_t S,
-                            int64_t stride, void* stream) {
-  SIMCLR_CHECK_ARG(x_hi && x_lo && wf_hi && wf_lo && y, "conv2d_fprop_tc3: null pointer");
+static const int kSplitPairs[6][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}, {0, 2}, {2, 0}};
+
+int simclr_conv2d_fprop_tc3(const void* x0, const void* x1, const void* x2, const void* w0, const void* w1,
+                            const void* w2, float* y, int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cout,
+                            int64_t R, int64_t S, int64_t stride, void* stream) {
+  SIMCLR_CHECK_ARG(x0 && x1 && x2 && w0 && w1 && w2 && y, "conv2d_fprop_tc3: null pointer");
   SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cs > 0 && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
                    "conv2d_fprop_tc3: bad geometry");
   const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  const void* xs[3] = {x_hi, x_hi, x_lo};
-  const void* ws[3] = {wf_hi, wf_lo, wf_hi};
-  for (int p = 0; p < 3; ++p) {
-    int rc = tc::run_igemm(0, xs[p], ws[p], y, SIMCLR_BF16, SIMCLR_F32, N, H, W, Cs, Ho, Wo, Cout, R, S, stride,
-                           (cudaStream_t)stream, "conv2d_fprop_tc3", nullptr, p > 0);
+  const void* xs[3] = {x0, x1, x2};
+  const void* ws[3] = {w0, w1, w2};
+  for (int p = 0; p < 6; ++p) {
+    int rc = tc::run_igemm(0, xs[kSplitPairs[p][0]], ws[kSplitPairs[p][1]], y, SIMCLR_BF16, SIMCLR_F32, N, H, W, Cs, Ho, Wo,
+                           Cout, R, S, stride, (cudaStream_t)stream, "conv2d_fprop_tc3", nullptr, p > 0);
     if (rc) return rc;
   }
   return SIMCLR_OK;
 }
 
-int simclr_conv2d_dgrad_tc3(const void* dy_hi, const void* dy_lo, const void* wd_hi, const void* wd_lo, float* dx,
-                            int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t R, int64_t S,
-                            int64_t stride, void* stream) {
-  SIMCLR_CHECK_ARG(dy_hi && dy_lo && wd_hi && wd_lo && dx, "conv2d_dgrad_tc3: null pointer");
+int simclr_conv2d_dgrad_tc3(const void* dy0, const void* dy1, const void* dy2, const void* w0, const void* w1,
+                            const void* w2, float* dx, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                            int64_t R, int64_t S, int64_t stride, void* stream) {
+  SIMCLR_CHECK_ARG(dy0 && dy1 && dy2 && w0 && w1 && w2 && dx, "conv2d_dgrad_tc3: null pointer");
   SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && R > 0 && S > 0 && (R & 1) && (S & 1) && stride > 0,
                    "conv2d_dgrad_tc3: bad geometry");
   const int64_t Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  const void* ds[3] = {dy_hi, dy_hi, dy_lo};
-  const void* ws[3] = {wd_hi, wd_lo, wd_hi};
-  for (int p = 0; p < 3; ++p) {
+  const void* ds[3] = {dy0, dy1, dy2};
+  const void* ws[3] = {w0, w1, w2};
+  for (int p = 0; p < 6; ++p) {
+    const void* d = ds[kSplitPairs[p][0]];
+    const void* w = ws[kSplitPairs[p][1]];
     int rc;
     if (stride > 1) {
-      if (!(stride <= 3 && Cout % 64 == 0 && simclr::aligned16(ds[p]) && simclr::aligned16(ws[p]) && simclr::aligned16(dx))) {
+      if (!(stride <= 3 && Cout % 64 == 0 && simclr::aligned16(d) && simclr::aligned16(w) && simclr::aligned16(dx))) {
         simclr::set_error("conv2d_dgrad_tc3: stride %lld needs Cout %% 64 == 0, stride <= 3 and 16-byte aligned operands", (long long)stride);
         return SIMCLR_ERR_UNSUPPORTED;
       }
-      rc = tc::run_dgrad_strided(ds[p], ws[p], dx, SIMCLR_BF16, SIMCLR_F32, N, H, W, Cin, Cout, R, S, stride,
-                                 (cudaStream_t)stream, p > 0);
+      rc = tc::run_dgrad_strided(d, w, dx, SIMCLR_BF16, SIMCLR_F32, N, H, W, Cin, Cout, R, S, stride, (cudaStream_t)stream, p > 0);
     } else {
-      rc = tc::run_igemm(1, ds[p], ws[p], dx, SIMCLR_BF16, SIMCLR_F32, N, Ho, Wo, Cout, H, W, Cin, R, S, stride,
+      rc = tc::run_igemm(1, d, w, dx, SIMCLR_BF16, SIMCLR_F32, N, Ho, Wo, Cout, H, W, Cin, R, S, stride,
                          (cudaStream_t)stream, "conv2d_dgrad_tc3", nullptr, p > 0);
     }
     if (rc) return rc;
@@ -1311,14 +1321,15 @@ int simclr_conv2d_dgrad_tc3(const void* dy_hi, const void* dy_lo, const void* wd
   return SIMCLR_OK;
 }
 
-int simclr_conv2d_wgrad_tc3(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw,
-                            int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cin, int64_t Cout, int64_t R,
-                            int64_t S, int64_t stride, void* stream) {
-  SIMCLR_CHECK_ARG(x_hi && x_lo && dy_hi && dy_lo && dw, "conv2d_wgrad_tc3: null pointer");
-  const void* xs[3] = {x_hi, x_hi, x_lo};
-  const void* ds[3] = {dy_hi, dy_lo, dy_hi};
-  for (int p = 0; p < 3; ++p) {
-    int rc = wgrad_tc_impl(xs[p], ds[p], dw, SIMCLR_BF16, N, H, W, Cs, Cin, Cout, R, S, stride, stream, p == 0);
+int simclr_conv2d_wgrad_tc3(const void* x0, const void* x1, const void* x2, const void* dy0, const void* dy1,
+                            const void* dy2, float* dw, int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cin,
+                            int64_t Cout, int64_t R, int64_t S, int64_t stride, void* stream) {
+  SIMCLR_CHECK_ARG(x0 && x1 && x2 && dy0 && dy1 && dy2 && dw, "conv2d_wgrad_tc3: null pointer");
+  const void* xs[3] = {x0, x1, x2};
+  const void* ds[3] = {dy0, dy1, dy2};
+  for (int p = 0; p < 6; ++p) {
+    int rc = wgrad_tc_impl(xs[kSplitPairs[p][0]], ds[kSplitPairs[p][1]], dw, SIMCLR_BF16, N, H, W, Cs, Cin, Cout, R, S, stride,
+                           stream, p == 0);
     if (rc) return rc;
   }
   return SIMCLR_OK;

@@ -166,9 +166,18 @@ class Engine:
         self.act_dtype = torch.bfloat16 if precision == 'bf16' else torch.float32
         self.conv_engine = conv_engine or FLAGS.b200_conv_engine
         if self.conv_engine == 'tc3' and self.act_dtype != torch.float32:
-            raise ValueError("b200_conv_engine='tc3' (BF16x3) is the fp32-storage mode: use --b200_precision=fp32")
+            raise ValueError("b200_conv_engine='tc3' (split-bf16 products) is the fp32-storage mode: use --b200_precision=fp32")
         self.ctx = ctx or ReplicaContext()
         self.profile = None        # list of per-launch (kind, shape, flops, ev0, ev1) when profiling
+        # per-step pools: BatchNorm sums (fp64) handed out in call order and zeroed ONCE per step together
+        # with the flat gradient buffer, instead of one memset per layer call (~170 per ResNet-50 step)
+        self._sums_pool = None
+        self._sums_cursor = 0
+        self.in_step = False
+        # conv / dense layers whose packed bf16 operands are refreshed by one multi-layer launch per forward
+        self._pack_ops = []
+        self._pack_table = None
+        self.pack_token = None
 
     # -- helpers ---------------------------------------------------------
     def code(self, dtype):
@@ -179,6 +188,65 @@ class Engine:
 
     def zeros(self, shape, dtype=None):
         return torch.zeros(shape, dtype=dtype or self.act_dtype, device=self.device)
+
+    SUMS_POOL_DOUBLES = 2 << 20        # 16 MB: ResNet-152 2x SK needs 0.75 M doubles per step
+
+    def begin_step(self, flat_grad=None):
+        """Zeroes the pooled accumulation buffers with two memsets and tells the library that its
+        per-call memsets are not needed until `end_step`."""
+        st = stream_ptr()
+        if self._sums_pool is None:
+            self._sums_pool = torch.empty(self.SUMS_POOL_DOUBLES, dtype=torch.float64, device=self.device)
+        self._sums_cursor = 0
+        lib.memset_zero(self._sums_pool, self._sums_pool.numel() * 8, st)
+        if flat_grad is not None:
+            lib.memset_zero(flat_grad, flat_grad.numel() * 4, st)
+        lib.set_accumulate_prezeroed(1)
+        self.in_step = True
+
+    def end_step(self):
+        lib.set_accumulate_prezeroed(0)
+        self.in_step = False
+
+    def sums(self, n):
+        """[n] fp64 accumulator for BatchNorm sums: a slice of the pre-zeroed pool inside a step, else a fresh
+        tensor (the library zeroes it in the call that fills it)."""
+        if not self.in_step:
+            return torch.empty(n, dtype=torch.float64, device=self.device)
+        n_al = (n + 1) // 2 * 2
+        if self._sums_cursor + n_al > self._sums_pool.numel():
+            raise SimclrError('BatchNorm sums pool exhausted (%d doubles)' % self._sums_pool.numel())
+        t = self._sums_pool[self._sums_cursor:self._sums_cursor + n]
+        self._sums_cursor += n_al
+        return t
+
+    # -- packed tcgen05 operands -------------------------------------------------
+    def register_packed(self, op):
+        self._pack_ops.append(op)
+        self._pack_table = None
+
+    def pack_all(self):
+        """One launch refreshing the packed bf16 operands of every registered layer from the fp32 masters;
+        returns False when there is nothing registered yet (first forward: layers pack themselves)."""
+        ops = [op for op in self._pack_ops if op.wf is not None and op.wf.dtype == torch.bfloat16]
+        if not ops or self.conv_engine != 'tc' or self.act_dtype != torch.bfloat16:
+            return False
+        if self._pack_table is None or self._pack_table[1] != len(ops):
+            rows = []
+            for op in ops:
+                Kp = op.wf.shape[1]
+                Kdp = op.wd.shape[1] if op.wd is not None else 0
+                rows.append([op.kernel.value.data_ptr(), op.wf.data_ptr(), op.wd.data_ptr() if op.wd is not None else 0,
+                             op.R, op.S, op.cin, op.cs, op.cout, Kp, Kdp])
+            self._pack_table = (torch.tensor(rows, dtype=torch.int64).to(self.device), len(ops), ops)
+        lib.pack_conv_weights_multi(self._pack_table[0], self._pack_table[1], stream_ptr())
+        self.pack_token = object()
+        for op in self._pack_table[2]:
+            op.packed_token = self.pack_token
+        return True
+
+    def pack_done(self):
+        self.pack_token = None
 
     @property
     def sync_bn(self):

@@ -90,7 +90,7 @@ def define_flags():
                   'Activation/operand storage type of the conv stack: bf16 (tcgen05 kind::f16, '
                   'fp32 accumulate) or fp32 (parity mode).')
     f.DEFINE_enum('b200_conv_engine', 'tc', ['tc', 'tc3', 'simt'],
-                  'tc: tcgen05/TMA implicit GEMM (default). tc3: BF16x3 split products on the tcgen05 engine '
+                  'tc: tcgen05/TMA implicit GEMM (default). tc3: three-way split-bf16 products on the tcgen05 engine '
                   '(fp32 storage, fp32-accurate: the tensor-core verification mode). '
                   'simt: CUDA-core fp32 verification engine.')
     f.DEFINE_integer('b200_num_classes', 1000, 'Classes of the supervised head when no dataset is read.')

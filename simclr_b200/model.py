@@ -107,7 +107,7 @@ class LinearLayer:
         rows = inputs.shape[0]
         y_dtype = out_dtype if (out_dtype is not None and not self.use_bn) else (
             torch.float32 if out_dtype == torch.float32 else None)
-        sums = e.empty((2 * self.num_classes,), torch.float64) if (self.use_bn and training) else None
+        sums = e.sums(2 * self.num_classes) if (self.use_bn and training) else None
         y = self.op.forward(inputs.view(rows, 1, 1, self.cin), training, out_dtype=y_dtype,
                             bn_sums=sums).view(rows, self.num_classes)
         if self.bias is not None:
@@ -240,13 +240,17 @@ class Model:
         # cast to the activation dtype and pad 3 -> 4 channels: one fused prep pass.
         features = data_util.prepare_views(inputs, num_transforms, use_blur, FLAGS.image_size,
                                            draws=self._blur_draws)
-        hiddens = self.resnet_model(features, training=training, endpoints=endpoints)
-        projection_head_outputs, supervised_head_inputs = self._projection_head(hiddens, training)
-        if FLAGS.train_mode == 'pretrain' and FLAGS.lineareval_while_pretraining:
-            # stop_gradient: nothing flows back from the supervised head (tf2/model.py:272-278)
-            supervised_head_outputs = self.supervised_head(supervised_head_inputs, training)
-            return projection_head_outputs, supervised_head_outputs
-        return projection_head_outputs, None
+        e.pack_all()         # bf16 operands of every conv / dense layer from the fp32 masters: one launch
+        try:
+            hiddens = self.resnet_model(features, training=training, endpoints=endpoints)
+            projection_head_outputs, supervised_head_inputs = self._projection_head(hiddens, training)
+            supervised_head_outputs = None
+            if FLAGS.train_mode == 'pretrain' and FLAGS.lineareval_while_pretraining:
+                # stop_gradient: nothing flows back from the supervised head (tf2/model.py:272-278)
+                supervised_head_outputs = self.supervised_head(supervised_head_inputs, training)
+        finally:
+            e.pack_done()
+        return projection_head_outputs, supervised_head_outputs
 
     def backward(self, d_projection_head_outputs, d_supervised_head_outputs=None):
         """Explicit `tape.gradient` (tf2/run.py:621): fills `.grad` of every trainable variable."""

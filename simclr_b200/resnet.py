@@ -47,7 +47,7 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
         b = None if self.beta is None else self.beta.value
         if training:
             if sums is None:
-                sums = e.empty((2 * C,), torch.float64)
+                sums = e.sums(2 * C)
                 lib.bn_stats(y, e.code(y.dtype), rows, C, sums, st)
             count = float(rows)
             if e.sync_bn and e.ctx.comm is not None and 2 * C * 8 <= e.ctx.comm.slot_bytes:
@@ -67,11 +67,17 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
             mean.copy_(self.moving_mean.value); rstd.copy_(r); scale.copy_(sc)
             shift.copy_(-self.moving_mean.value * sc if b is None else b - self.moving_mean.value * sc)
         z = e.empty(y.shape, out_dtype or y.dtype)
-        lib.bn_apply(y, e.code(y.dtype), residual, z, e.code(z.dtype), rows, C, scale, shift, int(relu), st)
+        tail = relu and residual is not None
+        bits = None
+        if tail and training:
+            # block tail: the ReLU mask is kept as one bit per element for the backward reduction
+            bits = e.empty((rows * C // 8,), torch.uint8)
+            lib.bn_apply_relu_mask(y, e.code(y.dtype), residual, z, e.code(z.dtype), rows, C, scale, shift, bits, st)
+        else:
+            lib.bn_apply(y, e.code(y.dtype), residual, z, e.code(z.dtype), rows, C, scale, shift, int(relu), st)
         if training:
             # BN+ReLU without residual: the backward recomputes the mask from y (scale, shift)
-            self.saved = (y, z if (relu and residual is not None) else None, mean, rstd, rows,
-                          (scale, shift) if (relu and residual is None) else None)
+            self.saved = (y, bits, mean, rstd, rows, (scale, shift) if (relu and residual is None) else None)
         return z
 
     def backward(self, dz, dz2=None, dy_dtype=None):
@@ -84,10 +90,11 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
         self.saved = None
         C = self.C
         st = stream_ptr()
-        sums = e.empty((2 * C,), torch.float64)
-        if zmask is not None:
-            assert zmask.dtype == dz.dtype
-        if remask is not None and dz2 is None:
+        sums = e.sums(2 * C)
+        if zmask is not None and zmask.dtype == torch.uint8 and remask is None:
+            lib.bn_bwd_reduce_bits(dz, dz2, zmask, e.code(dz.dtype), y, e.code(y.dtype), rows, C, mean, rstd, sums, st)
+            msc = msh = None
+        elif remask is not None and dz2 is None:
             lib.bn_bwd_relu_reduce(dz, e.code(dz.dtype), y, e.code(y.dtype), rows, C, mean, rstd,
                                    remask[0], remask[1], sums, st)
             msc, msh = remask
@@ -128,7 +135,8 @@ class ConvOp:
         self.cs = stored_cin or cin
         self.need_dgrad = need_dgrad
         self.wf = self.wd = None
-        self.wf_lo = self.wd_lo = None       # BF16x3: residual parts of the packed weights
+        self.wf3 = self.wd3 = None           # tc3: the three bf16 terms of the packed weights
+        self.packed_token = None             # == engine.pack_token: operands refreshed by the multi-layer launch
         self.saved_x = None
 
     def _pack(self, e):
@@ -141,28 +149,30 @@ class ConvOp:
             self.wf = e.empty((self.cout, Kp))
             kd = self.R * self.S * self.cout
             self.wd = e.empty((self.cin, (kd + kbe - 1) // kbe * kbe)) if self.need_dgrad else None
+            e.register_packed(self)
+        if e.pack_token is not None and self.packed_token is e.pack_token:
+            return                           # refreshed by engine.pack_all() at the start of this forward
         lib.pack_conv_weight(self.kernel.value, self.wf, self.wd, e.code(e.act_dtype), self.R, self.S, self.cin,
                              self.cs, self.cout, Kp, stream_ptr())
 
     def _pack3(self, e):
-        """BF16x3 operands: hi = bf16(w) in the ordinary packed layouts, lo = bf16(w - hi)."""
+        """Split-bf16 operands: the three bf16 terms of every weight in the ordinary packed layouts."""
         K = self.R * (self.S + 1 if self.cs == 4 else self.S) * self.cs
         Kp = (K + 63) // 64 * 64
-        if self.wf is None or self.wf.dtype != torch.bfloat16 or self.wf_lo is None:
+        if self.wf3 is None:
             kd = (self.R * self.S * self.cout + 63) // 64 * 64
-            self.wf = e.empty((self.cout, Kp), torch.bfloat16)
-            self.wf_lo = e.empty((self.cout, Kp), torch.bfloat16)
-            self.wd = e.empty((self.cin, kd), torch.bfloat16) if self.need_dgrad else None
-            self.wd_lo = e.empty((self.cin, kd), torch.bfloat16) if self.need_dgrad else None
+            self.wf3 = [e.empty((self.cout, Kp), torch.bfloat16) for _ in range(3)]
+            self.wd3 = [e.empty((self.cin, kd), torch.bfloat16) if self.need_dgrad else None for _ in range(3)]
         st = stream_ptr()
-        lib.pack_conv_weight(self.kernel.value, self.wf, self.wd, BF16, self.R, self.S, self.cin, self.cs, self.cout, Kp, st)
-        lib.pack_conv_weight_lo(self.kernel.value, self.wf_lo, self.wd_lo, self.R, self.S, self.cin, self.cs, self.cout, Kp, st)
+        for part in range(3):
+            lib.pack_conv_weight_part(self.kernel.value, self.wf3[part], self.wd3[part], part, self.R, self.S, self.cin,
+                                      self.cs, self.cout, Kp, st)
 
     @staticmethod
     def _split(e, t):
-        hi = e.empty(t.shape, torch.bfloat16); lo = e.empty(t.shape, torch.bfloat16)
-        lib.split_bf16x2(t, hi, lo, t.numel(), stream_ptr())
-        return hi, lo
+        parts = [e.empty(t.shape, torch.bfloat16) for _ in range(3)]
+        lib.split_bf16x3(t, parts[0], parts[1], parts[2], t.numel(), stream_ptr())
+        return parts
 
     def _timed(self, e, kind, x_shape, fn):
         """Optional per-launch CUDA-event timing (bench.py roofline pass)."""
@@ -192,11 +202,11 @@ class ConvOp:
             self._timed(e, 'fprop', x.shape, lambda: lib.conv2d_fprop_tc(
                 x, self.wf, y, e.code(x.dtype), e.code(y.dtype), N, H, W, Cs, self.cout, self.R, self.S, s, bn_sums, st))
         elif e.conv_engine == 'tc3':
-            assert x.dtype == torch.float32 and y.dtype == torch.float32, 'BF16x3 is the fp32-storage mode'
+            assert x.dtype == torch.float32 and y.dtype == torch.float32, 'tc3 (split bf16) is the fp32-storage mode'
             self._pack3(e)
             xs = self._split(e, x)
             self._timed(e, 'fprop', x.shape, lambda: lib.conv2d_fprop_tc3(
-                xs[0], xs[1], self.wf, self.wf_lo, y, N, H, W, Cs, self.cout, self.R, self.S, s, st))
+                xs[0], xs[1], xs[2], self.wf3[0], self.wf3[1], self.wf3[2], y, N, H, W, Cs, self.cout, self.R, self.S, s, st))
             if bn_sums is not None:
                 lib.bn_stats(y, e.code(y.dtype), y.numel() // self.cout, self.cout, bn_sums, st)
             if training:
@@ -246,25 +256,27 @@ class ConvOp:
 
 
 def _convop_backward_tc3(self, e, saved, dy, need_dx, dx_dtype):
-    x, (xh, xl) = saved
+    x, xs = saved
     N, H, W, Cs = x.shape
     st = stream_ptr()
     assert dy.dtype == torch.float32
+    ds = None
     if self.cout % 8 == 0:
-        dh, dl = self._split(e, dy)
+        ds = self._split(e, dy)
         self._timed(e, 'wgrad', x.shape, lambda: lib.conv2d_wgrad_tc3(
-            xh, xl, dh, dl, self.kernel.grad, N, H, W, Cs, self.cin, self.cout, self.R, self.S, self.stride, st))
+            xs[0], xs[1], xs[2], ds[0], ds[1], ds[2], self.kernel.grad, N, H, W, Cs, self.cin, self.cout, self.R, self.S,
+            self.stride, st))
     else:       # odd-width supervised head: 16-byte rows of dY are a tcgen05 wgrad requirement
-        dh = dl = None
         lib.conv2d_wgrad_simt(x, dy, self.kernel.grad, F32, N, H, W, Cs, self.cin, self.cout, self.R, self.S,
                               self.stride, st)
     if not (need_dx and self.need_dgrad):
         return None
-    if dh is None:
-        dh, dl = self._split(e, dy)
+    if ds is None:
+        ds = self._split(e, dy)
     dx = e.empty((N, H, W, self.cin), torch.float32)
     self._timed(e, 'dgrad', x.shape, lambda: lib.conv2d_dgrad_tc3(
-        dh, dl, self.wd, self.wd_lo, dx, N, H, W, self.cin, self.cout, self.R, self.S, self.stride, st))
+        ds[0], ds[1], ds[2], self.wd3[0], self.wd3[1], self.wd3[2], dx, N, H, W, self.cin, self.cout, self.R, self.S,
+        self.stride, st))
     return dx
 
 
@@ -278,7 +290,7 @@ def conv_bn(conv, bn, x, training, **bn_kwargs):
     op = conv.op if hasattr(conv, 'op') else conv
     if not training:
         return bn(op.forward(x, training), training, **bn_kwargs)
-    sums = e.empty((2 * op.cout,), torch.float64)
+    sums = e.sums(2 * op.cout)
     y = op.forward(x, training, bn_sums=sums)
     return bn(y, training, sums=sums, **bn_kwargs)
 

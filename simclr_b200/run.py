@@ -55,6 +55,14 @@ class Trainer:
         embedding / log-sum-exp all-gathers) are our own peer-memory kernels when
         `strategy.comm` is set, so this part is CUDA-graph capturable at any replica count."""
         e, model, R = self.engine, self.model, self.strategy.num_replicas_in_sync
+        e.begin_step(model.vs.flat_grad)       # BN-sum pool and the flat gradient buffer zeroed once
+        try:
+            return self._forward_backward(features, labels)
+        finally:
+            e.end_step()
+
+    def _forward_backward(self, features, labels):
+        e, model, R = self.engine, self.model, self.strategy.num_replicas_in_sync
         st = stream_ptr()
         projection_head_outputs, supervised_head_outputs = model(features, training=True)
         B = features.shape[0]

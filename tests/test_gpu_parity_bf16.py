@@ -21,7 +21,7 @@ the fixture.  What can be pinned, and is:
 3. a 20-step LARS trajectory tracks the fp32 oracle's loss curve as closely as the bf16-storage
    oracle's own trajectory does.
 On ResNet-18 (config 1) and on plain ResNet-50 bottlenecks (the benchmarked network family).
-The 1e-3 bar of the north_star is met on the tensor pipe by the BF16x3 mode (test_gpu_step.py::
+The 1e-3 bar of the north_star is met on the tensor pipe by the split-bf16 mode (tc3) (test_gpu_step.py::
 test_step_parity_tc3) and kernel by kernel in test_gpu_tc.py (2e-4 on bf16-representable inputs).
 """
 import collections

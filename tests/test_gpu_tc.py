@@ -35,6 +35,12 @@ CASES = [
     (2, 31, 31, 3, 4, 64, 7, 2),         # stem on an odd width: 8-byte gather (no pixel pairs)
     (2, 16, 16, 3, 4, 64, 3, 1),         # CIFAR stem: 3x3 stride 1 on 4 stored channels
     (3, 20, 28, 3, 4, 64, 7, 2),         # stem, rectangular, pixel-pair path, ragged last tile
+    # halo-reuse 3x3 kernel (tc_halo.cu): bf16 in/out, 64->64 (resident filter) and 128->128 (streamed filter)
+    (2, 56, 56, 64, 64, 64, 3, 1),       # the ResNet-50 stage-1 3x3: Wp 58, 2 rows per tile
+    (3, 28, 28, 128, 128, 128, 3, 1),    # stage-2 3x3: Wp 30, 4 rows per tile, two channel blocks
+    (2, 27, 28, 128, 128, 128, 3, 1),    # H not a multiple of the rows per tile: last tile clipped by the TMA store
+    (5, 18, 30, 64, 64, 64, 3, 1),       # Wp 32, more tiles than one wave of a small grid
+    (1, 10, 62, 64, 64, 64, 3, 1),       # widest supported row (Wp 64)
 ]
 
 
@@ -170,16 +176,16 @@ def test_tc_matches_simt_large(shape):
 def _split(t):
     from simclr_b200._lib import lib, stream_ptr
     t = t.float().cuda().contiguous()
-    hi = torch.empty(t.shape, dtype=torch.bfloat16, device='cuda'); lo = torch.empty_like(hi)
-    lib.split_bf16x2(t, hi, lo, t.numel(), stream_ptr())
-    return hi, lo
+    parts = [torch.empty(t.shape, dtype=torch.bfloat16, device='cuda') for _ in range(3)]
+    lib.split_bf16x3(t, parts[0], parts[1], parts[2], t.numel(), stream_ptr())
+    return parts
 
 
 @pytest.mark.parametrize('case', [CASES[i] for i in (0, 1, 2, 4, 5, 6, 8, 12, 13, 16)])
-def test_tc3_bf16x3_fp32_accuracy(case):
-    """BF16x3 (fp32 operands split hi + lo, three tcgen05 GEMMs summed in fp32): fprop, dgrad and wgrad
-    against the fp64 oracle conv on UNROUNDED fp32 inputs at 2e-5 -- two orders below a single bf16 pass
-    (4e-3) and at the level of an fp32 CUDA-core conv."""
+def test_tc3_split_bf16_fp32_accuracy(case):
+    """tc3 (fp32 operands split into three bf16 terms, six tcgen05 GEMMs summed in fp32): fprop, dgrad and
+    wgrad against the fp64 oracle conv on UNROUNDED fp32 inputs at 5e-6 -- three orders below a single
+    bf16 pass (4e-3), at the level of an fp32 CUDA-core conv."""
     from simclr_b200._lib import lib, stream_ptr
     N, H, W, Cin, Cs, Cout, k, s = case
     x, w, xs = _mk(case, torch.float32, 11)
@@ -187,30 +193,47 @@ def test_tc3_bf16x3_fp32_accuracy(case):
     yo = conv_reference(xo, wo, k, s)
     dy = torch.randn(yo.shape)
     yo.backward(dy.double())
-    xh, xl = _split(xs)
-    assert rel_err(xh.float() + xl.float(), xs) < 1e-5          # hi + lo carries 16 mantissa bits
+    xp = _split(xs)
+    assert torch.equal((xp[0].double() + xp[1].double() + xp[2].double()).float().cpu(), xs)     # 24 mantissa bits recovered
     K = k * (k + 1 if Cs == 4 else k) * Cs
     Kp = (K + 63) // 64 * 64
     kd = (k * k * Cout + 63) // 64 * 64
-    wf = torch.empty(Cout, Kp, dtype=torch.bfloat16, device='cuda'); wfl = torch.empty_like(wf)
     has_wd = Cs == Cin
-    wd = torch.empty(Cin, kd, dtype=torch.bfloat16, device='cuda') if has_wd else None
-    wdl = torch.empty_like(wd) if has_wd else None
+    wf = [torch.empty(Cout, Kp, dtype=torch.bfloat16, device='cuda') for _ in range(3)]
+    wd = [torch.empty(Cin, kd, dtype=torch.bfloat16, device='cuda') if has_wd else None for _ in range(3)]
     wc = w.float().cuda().contiguous()
-    lib.pack_conv_weight(wc, wf, wd, 1, k, k, Cin, Cs, Cout, Kp, stream_ptr())
-    lib.pack_conv_weight_lo(wc, wfl, wdl, k, k, Cin, Cs, Cout, Kp, stream_ptr())
+    for part in range(3):
+        lib.pack_conv_weight_part(wc, wf[part], wd[part], part, k, k, Cin, Cs, Cout, Kp, stream_ptr())
     y = torch.full(yo.shape, float('nan'), dtype=torch.float32, device='cuda')
-    lib.conv2d_fprop_tc3(xh, xl, wf, wfl, y, N, H, W, Cs, Cout, k, k, s, stream_ptr())
+    lib.conv2d_fprop_tc3(xp[0], xp[1], xp[2], wf[0], wf[1], wf[2], y, N, H, W, Cs, Cout, k, k, s, stream_ptr())
     torch.cuda.synchronize()
-    assert rel_err(y, yo) < 2e-5
-    dh, dl = _split(dy)
+    assert rel_err(y, yo) < 5e-6
+    dp = _split(dy)
     if Cout % 8 == 0:
         dw = torch.full((k, k, Cin, Cout), float('nan'), dtype=torch.float32, device='cuda')
-        lib.conv2d_wgrad_tc3(xh, xl, dh, dl, dw, N, H, W, Cs, Cin, Cout, k, k, s, stream_ptr())
+        lib.conv2d_wgrad_tc3(xp[0], xp[1], xp[2], dp[0], dp[1], dp[2], dw, N, H, W, Cs, Cin, Cout, k, k, s, stream_ptr())
         torch.cuda.synchronize()
-        assert rel_err(dw, wo.grad) < 2e-5
+        assert rel_err(dw, wo.grad) < 5e-6
     if has_wd:
         dx = torch.full((N, H, W, Cin), float('nan'), dtype=torch.float32, device='cuda')
-        lib.conv2d_dgrad_tc3(dh, dl, wd, wdl, dx, N, H, W, Cin, Cout, k, k, s, stream_ptr())
+        lib.conv2d_dgrad_tc3(dp[0], dp[1], dp[2], wd[0], wd[1], wd[2], dx, N, H, W, Cin, Cout, k, k, s, stream_ptr())
         torch.cuda.synchronize()
-        assert rel_err(dx, xo.grad) < 2e-5
+        assert rel_err(dx, xo.grad) < 5e-6
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c[6] == 3 and c[7] == 1 and c[3] == c[5] and c[3] in (64, 128)])
+def test_tc_dgrad_bf16_out(case):
+    """Stride-1 3x3 dgrad with bf16 output -- the dtype of the training step, and the only one the
+    halo-reuse kernel serves (flipped taps over a dY slab)."""
+    from simclr_b200._lib import lib, stream_ptr
+    N, H, W, Cin, Cs, Cout, k, s = case
+    x, w, xs = _mk(case, torch.bfloat16)
+    xo = x.double().requires_grad_(True)
+    yo = conv_reference(xo, w.double(), k, s)
+    dy = torch.randn(yo.shape).to(torch.bfloat16)
+    yo.backward(dy.double())
+    _, wd = _pack(w, torch.bfloat16, k, Cin, Cs, Cout)
+    dx = torch.full((N, H, W, Cin), float('nan'), dtype=torch.bfloat16, device='cuda')
+    lib.conv2d_dgrad_tc(dy.cuda(), wd, dx, 1, 1, N, H, W, Cin, Cout, k, k, s, stream_ptr())
+    torch.cuda.synchronize()
+    assert rel_err(dx, xo.grad) < 8e-3
