@@ -340,6 +340,14 @@ SIMCLR_API int simclr_augment(const uint8_t* src, const int64_t* src_offset, con
                               int64_t n, int64_t height, int64_t width, int64_t out_pixel_stride,
                               int64_t out_channel_offset, void* stream);
 
+/* The other optimizers of build_optimizer (tf2/model.py:29-44), element-wise over flat buffers of n floats.
+ * hyper_dev: device float[1] staged by the caller (stream-ordered): SGD {lr}; Adam
+ * {lr * sqrt(1 - beta2^t) / (1 - beta1^t)} with t the 1-based step. */
+SIMCLR_API int simclr_sgd_momentum_apply(float* w, const float* g, float* v, int64_t n, const float* hyper_dev,
+                                         float momentum, int nesterov, void* stream);
+SIMCLR_API int simclr_adam_apply(float* w, const float* g, float* m, float* v, int64_t n, const float* hyper_dev,
+                                 float beta1, float beta2, float eps, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Collectives over NVLink peer memory, fused into the kernels that consume them (no NCCL on these
  * paths).  Every rank owns one allocation of identical layout that all peers have

@@ -204,6 +204,27 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
   return d;
 }
+// The same descriptor from its two 32-bit halves: only the 14-bit start-address field (bytes >> 4) changes between
+// the MMAs of a tile, so the issuing warp keeps `lo` as a running 32-bit value (one add per MMA, computed
+// warp-uniformly so that it lives in a uniform register) instead of rebuilding 64 bits from an address.
+__host__ __device__ constexpr uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+  uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi)); return d;
+}
+// one lane of a converged warp (the form the compiler recognises for single-thread tcgen05 issue)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+// value of lane 0, provably warp-uniform for the compiler
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // Instruction descriptor for kind::f16 (bf16) / kind::tf32, fp32 accumulate.
 __host__ __device__ constexpr uint32_t make_idesc(bool tf32, int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4)                               // c_format = F32

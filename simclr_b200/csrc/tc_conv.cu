@@ -353,24 +353,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
   } else if (warp == 4) {
     // ------------------------------ MMA issuer ----------------------------
+    // All lanes run the loop on warp-uniform values; the descriptor low words are running 32-bit sums (one
+    // uniform add per MMA) and one elected lane issues the four MMAs of a stage back to back.  Building each
+    // 64-bit descriptor from an address inside `if (lane == 0)` cost ~20 SASS instructions per MMA and paced
+    // short-N tiles at ~130 cycles per MMA instead of 32-128 (profiles/r02_ncu_halo.txt).
+    constexpr uint32_t HI = desc_hi_sw128(1024);
     Pipe pp{0, 0};
     int as = 0; uint32_t aphase = 0;
+    const uint32_t smem_lo = uniform_u32(desc_lo(smem_u32(smem), 16));
+    const uint32_t tmem_u = uniform_u32(tmem_base);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&ctl.tmem_empty[as], aphase ^ 1, 20);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      const uint32_t d_tmem = tmem_u + (uint32_t)(as * BN);
       for (int kb = 0; kb < g.num_kb; ++kb) {
         mbar_wait(&ctl.full[pp.stage], pp.phase, 21);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + (size_t)pp.stage * TL::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+        const uint32_t a_lo = smem_lo + (uint32_t)pp.stage * (TL::STAGE_BYTES >> 4);
+        const uint32_t b_lo = a_lo + (A_STAGE_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {      // 4 x (32 bytes of K) per stage
-            const uint64_t ad = smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma<TF32>(d_tmem, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)        // 4 x (32 bytes of K) per stage
+            umma<TF32>(d_tmem, desc_pack(a_lo + 2 * k, HI), desc_pack(b_lo + 2 * k, HI), IDESC, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&ctl.empty[pp.stage]);            // frees the smem slot when the MMAs retire
           if (kb == g.num_kb - 1) umma_commit(&ctl.tmem_full[as]);
         }
@@ -688,27 +692,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     }
     if (TMA_RED && threadIdx.x == 0) tma_store_wait_all<0>();
   } else if (warp == 4) {
+    // MN-major operands: LBO = distance between 128-byte-wide atoms along M/N, SBO = 8 pixel rows; uniform
+    // running descriptor words, one elected lane issues the four MMAs of a stage (see igemm_kernel)
+    constexpr uint32_t HI = desc_hi_sw128(1024);
     Pipe pp{0, 0};
     int as = 0; uint32_t aphase = 0;
+    const uint32_t smem_lo = uniform_u32(desc_lo(smem_u32(smem), ATOM_BYTES));
+    const uint32_t tmem_u = uniform_u32(tmem_base);
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int tk, tn, kb0, kb1; decode(item, tk, tn, kb0, kb1);
       if (kb0 >= kb1) continue;
       mbar_wait(&ctl.tmem_empty[as], aphase ^ 1, 60);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      const uint32_t d_tmem = tmem_u + (uint32_t)(as * BN);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&ctl.full[pp.stage], pp.phase, 61);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + (size_t)pp.stage * TL::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+        const uint32_t a_lo = smem_lo + (uint32_t)pp.stage * (TL::STAGE_BYTES >> 4);
+        const uint32_t b_lo = a_lo + (A_STAGE_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // MN-major: LBO = distance between 128-byte-wide atoms along M/N, SBO = 8 pixel rows
-            const uint64_t ad = smem_desc_sw128(a_addr + k * UMMA_K * 128, ATOM_BYTES, 1024);
-            const uint64_t bd = smem_desc_sw128(b_addr + k * UMMA_K * 128, ATOM_BYTES, 1024);
-            umma<TF32>(d_tmem, ad, bd, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma<TF32>(d_tmem, desc_pack(a_lo + k * (UMMA_K * 128 >> 4), HI), desc_pack(b_lo + k * (UMMA_K * 128 >> 4), HI), IDESC,
+                       (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&ctl.empty[pp.stage]);
           if (kb == kb1 - 1) umma_commit(&ctl.tmem_full[as]);
         }

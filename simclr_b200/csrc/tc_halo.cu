@@ -32,8 +32,8 @@ struct HaloGeom {
   int tiles_per_img, num_tiles;
   int box_bytes;               // bytes one slab TMA box delivers ((TR+2) * Wp * 128)
   int n_out;                   // output channels
-  int pix_off[9];              // tap -> pixel offset of the A window in the slab
-  int kcol[9];                 // tap -> first K column of the tap in the packed filter
+  int tap_base, tap_sign;      // pixel offset of the A window of tap (r, s) in the slab: tap_base + tap_sign*(r*Wp + s)
+  int C;                       // input channels: tap t starts at K column t*C of the packed filter
 };
 
 template <int BN, int CB, bool B_RES> struct HaloCfg {
@@ -200,43 +200,51 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     if (threadIdx.x == 0) tma_store_wait_all<0>();
   } else if (warp == 4) {
     // ------------------------------ MMA issuer ----------------------------
+    // Every lane runs the loop on warp-uniform values (descriptor low words are running 32-bit sums in
+    // uniform registers); only the tcgen05 instructions are predicated on lane 0.  The first version built
+    // each 64-bit descriptor from an address inside `if (lane == 0)`: ~20 SASS instructions and a local-memory
+    // load per MMA, ~130 cycles against the 32-48 cycles an M128 x N64 x K16 MMA takes -- the tensor pipe sat
+    // at 13 % (profiles/r02_ncu_halo.txt).
+    constexpr uint32_t HI = desc_hi_sw128(1024);
     int ss = 0; uint32_t sphase = 0;
     int bs = 0; uint32_t bphase = 0;
     int as = 0; uint32_t aphase = 0;
+    const uint32_t slab0_lo = uniform_u32(desc_lo(smem_u32(slab), 16));
+    const uint32_t bt_lo = uniform_u32(desc_lo(smem_u32(bt), 16));
+    const uint32_t tmem_u = uniform_u32(tmem_base);
     if (B_RES) { mbar_wait(&b_full[0], 0, 120); }
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty[as], aphase ^ 1, 121);
       mbar_wait(&slab_full[ss], sphase, 122);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-      const uint32_t slab_addr = smem_u32(slab + (size_t)ss * CFG::SLAB_STAGE_BYTES);
-#pragma unroll 1
+      const uint32_t d_tmem = tmem_u + (uint32_t)(as * BN);
+      const uint32_t a_tile_lo = slab0_lo + (uint32_t)ss * (CFG::SLAB_STAGE_BYTES >> 4) + (uint32_t)g.tap_base * 8u;
+#pragma unroll
       for (int t = 0; t < 9; ++t) {
+        const int r = t / 3, sx = t % 3;
+        const uint32_t a_tap_lo = a_tile_lo + (uint32_t)(g.tap_sign * (r * g.Wp + sx)) * 8u;   // 128 B per pixel
 #pragma unroll
         for (int cb = 0; cb < CB; ++cb) {
-          uint32_t b_addr;
+          uint32_t b_lo;
           if (B_RES) {
-            b_addr = smem_u32(bt + (size_t)(t * CB + cb) * CFG::B_TILE);
+            b_lo = bt_lo + (uint32_t)(t * CB + cb) * (CFG::B_TILE >> 4);
           } else {
             mbar_wait(&b_full[bs], bphase, 123);
             tc_fence_after();
-            b_addr = smem_u32(bt + (size_t)bs * CFG::B_TILE);
+            b_lo = bt_lo + (uint32_t)bs * (CFG::B_TILE >> 4);
           }
-          if (lane == 0) {
-            const uint32_t a_addr = slab_addr + cb * SLAB_BYTES + (uint32_t)g.pix_off[t] * 128u;
+          const uint32_t a_lo = a_tap_lo + cb * (SLAB_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = smem_desc_sw128(a_addr + k * 32, 16, 1024);
-              const uint64_t bd = smem_desc_sw128(b_addr + k * 32, 16, 1024);
-              umma<false>(d_tmem, ad, bd, IDESC, (t | cb | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < 4; ++k)
+              umma<false>(d_tmem, desc_pack(a_lo + 2 * k, HI), desc_pack(b_lo + 2 * k, HI), IDESC, (t | cb | k) != 0 ? 1u : 0u);
             if (!B_RES) umma_commit(&b_empty[bs]);
           }
           __syncwarp();
           if (!B_RES) { if (++bs == BS) { bs = 0; bphase ^= 1; } }
         }
       }
-      if (lane == 0) { umma_commit(&slab_empty[ss]); umma_commit(&tmem_full[as]); }
+      if (elect_one()) { umma_commit(&slab_empty[ss]); umma_commit(&tmem_full[as]); }
       __syncwarp();
       if (++ss == SS) { ss = 0; sphase ^= 1; }
       as ^= 1; if (as == 0) aphase ^= 1;
@@ -248,7 +256,7 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         mbar_arrive_expect_tx(&b_full[0], 9 * CB * CFG::B_TILE);
         for (int t = 0; t < 9; ++t)
           for (int cb = 0; cb < CB; ++cb)
-            tma_load_2d(bt + (size_t)(t * CB + cb) * CFG::B_TILE, &tmap_w, &b_full[0], g.kcol[t] + cb * 64, 0);
+            tma_load_2d(bt + (size_t)(t * CB + cb) * CFG::B_TILE, &tmap_w, &b_full[0], t * g.C + cb * 64, 0);
       }
       int ss = 0; uint32_t sphase = 0;
       int bs = 0; uint32_t bphase = 0;
@@ -269,7 +277,7 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             for (int cb = 0; cb < CB; ++cb) {
               mbar_wait(&b_empty[bs], bphase ^ 1, 131);
               mbar_arrive_expect_tx(&b_full[bs], CFG::B_TILE);
-              tma_load_2d(bt + (size_t)bs * CFG::B_TILE, &tmap_w, &b_full[bs], g.kcol[t] + cb * 64, 0);
+              tma_load_2d(bt + (size_t)bs * CFG::B_TILE, &tmap_w, &b_full[bs], t * g.C + cb * 64, 0);
               if (++bs == BS) { bs = 0; bphase ^= 1; }
             }
         }
@@ -347,12 +355,9 @@ int run_halo3x3(int mode, const void* src, const void* wk, void* out, int64_t N,
   g.H = (int)H; g.W = (int)W; g.Wp = (int)W + 2; g.TR = 128 / g.Wp; g.N = (int)N;
   g.tiles_per_img = (int)((H + g.TR - 1) / g.TR); g.num_tiles = (int)(N * g.tiles_per_img);
   g.box_bytes = (g.TR + 2) * g.Wp * 128; g.n_out = (int)n_out;
-  for (int r = 0; r < 3; ++r)
-    for (int s = 0; s < 3; ++s) {
-      const int t = r * 3 + s;
-      g.kcol[t] = (int)(t * C);
-      g.pix_off[t] = mode == 0 ? r * g.Wp + s : (2 - r) * g.Wp + (2 - s);
-    }
+  g.C = (int)C;
+  g.tap_base = mode == 0 ? 0 : 2 * g.Wp + 2;        // dgrad: dX[p,q] = sum dY[p+1-r, q+1-s] W[r,s]: flipped window
+  g.tap_sign = mode == 0 ? 1 : -1;
   const int64_t K = 9 * C;
   CUtensorMap tx, tw, ty;
   int rc = make_tmap_nhwc_tiled(&tx, src, (uint64_t)N, (uint64_t)H, (uint64_t)W, (uint64_t)C, (uint32_t)g.Wp, (uint32_t)(g.TR + 2));

@@ -225,20 +225,25 @@ class Engine:
         self._pack_ops.append(op)
         self._pack_table = None
 
+    def _pack_ops_ready(self):
+        return [op for op in self._pack_ops if op.wf is not None and op.wf.dtype == torch.bfloat16]
+
+    def _build_pack_table(self):
+        ops = self._pack_ops_ready()
+        rows = []
+        for op in ops:
+            Kp = op.wf.shape[1]
+            Kdp = op.wd.shape[1] if op.wd is not None else 0
+            rows.append([op.kernel.value.data_ptr(), op.wf.data_ptr(), op.wd.data_ptr() if op.wd is not None else 0,
+                         op.R, op.S, op.cin, op.cs, op.cout, Kp, Kdp])
+        self._pack_table = (torch.tensor(rows, dtype=torch.int64).to(self.device), len(ops), ops)
+
     def pack_all(self):
         """One launch refreshing the packed bf16 operands of every registered layer from the fp32 masters;
-        returns False when there is nothing registered yet (first forward: layers pack themselves)."""
-        ops = [op for op in self._pack_ops if op.wf is not None and op.wf.dtype == torch.bfloat16]
-        if not ops or self.conv_engine != 'tc' or self.act_dtype != torch.bfloat16:
+        returns False when the table does not exist yet (first forward: layers pack themselves, `pack_done`
+        builds the table afterwards -- a host-to-device copy, so never inside a graph capture)."""
+        if self.conv_engine != 'tc' or self.act_dtype != torch.bfloat16 or self._pack_table is None:
             return False
-        if self._pack_table is None or self._pack_table[1] != len(ops):
-            rows = []
-            for op in ops:
-                Kp = op.wf.shape[1]
-                Kdp = op.wd.shape[1] if op.wd is not None else 0
-                rows.append([op.kernel.value.data_ptr(), op.wf.data_ptr(), op.wd.data_ptr() if op.wd is not None else 0,
-                             op.R, op.S, op.cin, op.cs, op.cout, Kp, Kdp])
-            self._pack_table = (torch.tensor(rows, dtype=torch.int64).to(self.device), len(ops), ops)
         lib.pack_conv_weights_multi(self._pack_table[0], self._pack_table[1], stream_ptr())
         self.pack_token = object()
         for op in self._pack_table[2]:
@@ -247,6 +252,9 @@ class Engine:
 
     def pack_done(self):
         self.pack_token = None
+        if self._pack_table is None and self._pack_ops_ready() and self.conv_engine == 'tc' and \
+                not torch.cuda.is_current_stream_capturing():
+            self._build_pack_table()
 
     @property
     def sync_bn(self):
