@@ -364,6 +364,14 @@ class Resnet:
         self.cout = cin
 
     def __call__(self, P, S, x_nhwc, training, endpoints=None):
+        cfg = self.cfg
+        # Finetuning with fine_tune_after_block = k >= 0 (tf2/resnet.py:548-549,619-692): the stem and block groups
+        # 1..k are `trainable=False` Keras layers -- their BatchNorm runs in inference mode [TF semantics] -- and a
+        # tf.stop_gradient sits in front of group k+1 (:675-681).  The caller leaves the frozen variables out of
+        # the optimizer (`frozen_variable_names`).
+        ft = cfg.fine_tune_after_block if cfg.train_mode == 'finetune' else -1
+        train_all = training
+        training = train_all and ft < 0
         x = q(x_nhwc.permute(0, 3, 1, 2))      # (emulation: the network input is cast to bf16)
         for layer in self.stem:
             x = layer(P, S, x, training)
@@ -374,13 +382,32 @@ class Resnet:
         if endpoints is not None:
             endpoints['initial_max_pool'] = x
         for i, g in enumerate(self.groups):
-            x = g(P, S, x, training)
+            if ft == i:
+                x = x.detach()                                  # tf.stop_gradient, :675-677
+            x = g(P, S, x, train_all and not (ft >= 0 and i < ft))
             if endpoints is not None:
                 endpoints['block_group%d' % (i + 1)] = x
+        if ft == 4:
+            x = x.detach()                                      # :680-681
         x = q(x.mean(dim=(2, 3)))                               # :693-696
         if endpoints is not None:
             endpoints['final_avg_pool'] = x
         return x
+
+
+def frozen_variable_names(cfg, names):
+    """Variables of `trainable=False` layers in a finetuning run (tf2/resnet.py:548-549,619-692)."""
+    ft = cfg.fine_tune_after_block if cfg.train_mode == 'finetune' else -1
+    if ft < 0:
+        return set()
+    out = set()
+    for n in names:
+        if not n.startswith('resnet/'):
+            continue
+        grp = [i for i in range(1, 5) if '/block_group%d/' % i in n]
+        if not grp or grp[0] <= ft:
+            out.add(n)
+    return out
 
 
 def resnet(vs, cfg, resnet_depth, width_multiplier, cifar_stem=False):

@@ -52,15 +52,23 @@ def forward_backward(model, P, S, features, labels, blur_draws=None):
                            blur_draws=None if blur_draws is None else blur_draws[r])
             proj.append(po)
             sup.append(so)
-    con = obj_lib.contrastive_loss_replicas(proj, cfg.hidden_norm, cfg.temperature)
+    if cfg.train_mode == 'finetune':
+        con = [None] * R                                          # supervised loss only (tf2/model.py:267-270)
+    else:
+        con = obj_lib.contrastive_loss_replicas(proj, cfg.hidden_norm, cfg.temperature)
     total = 0.
     con_losses, sup_losses = [], []
     wd = model_lib.add_weight_decay(cfg, Pg, adjust_per_optimizer=True)
     for r in range(R):
-        loss = con[r][0]
-        con_losses.append(con[r][0].detach())
+        loss = 0.
+        if con[r] is not None:
+            loss = con[r][0]
+            con_losses.append(con[r][0].detach())
         if sup[r] is not None:
-            l = torch.cat([labels[r], labels[r]], 0)
+            # tf2/run.py:600-602: the labels are doubled only when pretraining with the linear-eval head
+            l = labels[r]
+            if cfg.train_mode == 'pretrain' and cfg.lineareval_while_pretraining:
+                l = torch.cat([labels[r], labels[r]], 0)
             sl = obj_lib.add_supervised_loss(l, sup[r])
             sup_losses.append(sl.detach())
             loss = loss + sl
@@ -72,8 +80,9 @@ def forward_backward(model, P, S, features, labels, blur_draws=None):
         G[k] = torch.zeros_like(v) if g is None else g
     return dict(loss=total.detach(), con_loss=con_losses, sup_loss=sup_losses,
                 wd=wd.detach() if torch.is_tensor(wd) else wd, grads=G,
-                logits_con=[c[1].detach() for c in con], labels_con=[c[2] for c in con],
-                S_new=Sn, proj_out=[p.detach() for p in proj],
+                logits_con=[None if c is None else c[1].detach() for c in con],
+                labels_con=[None if c is None else c[2] for c in con],
+                S_new=Sn, proj_out=[None if p is None else p.detach() for p in proj],
                 sup_out=[None if s is None else s.detach() for s in sup])
 
 

@@ -57,8 +57,12 @@ class VarStore:
         self.trainable = []
         self.moving = []
         self.flat_value = self.flat_grad = self.flat_moving = None
+        # False while the layers of a frozen part are built (`trainable=False` Keras layers of a finetuning
+        # run, tf2/resnet.py:548-549,619-692): their variables join the non-trainable list
+        self.default_trainable = True
 
     def add(self, name, shape, init, trainable=True):
+        trainable = trainable and self.default_trainable
         v = Variable(name, shape, init, trainable)
         (self.trainable if trainable else self.moving).append(v)
         return v

@@ -95,6 +95,7 @@ def define_flags():
                   'simt: CUDA-core fp32 verification engine.')
     f.DEFINE_integer('b200_num_classes', 1000, 'Classes of the supervised head when no dataset is read.')
     f.DEFINE_integer('b200_num_examples', 1281167, 'Examples per epoch when no dataset is read.')
+    f.DEFINE_integer('b200_num_eval_examples', 50000, 'Evaluation examples when no dataset is read.')
 
 
 define_flags()

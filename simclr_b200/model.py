@@ -23,9 +23,12 @@ def build_optimizer(learning_rate):
             momentum=FLAGS.momentum,
             weight_decay=FLAGS.weight_decay,
             exclude_from_weight_decay=['batch_normalization', 'bias', 'head_supervised'])
-    elif FLAGS.optimizer in ('momentum', 'adam'):
-        raise NotImplementedError(
-            "optimizer=%r: only 'lars' (the pretraining optimizer) is on the B200 path" % FLAGS.optimizer)
+    elif FLAGS.optimizer == 'momentum':
+        from . import optimizers
+        return optimizers.SGD(learning_rate, FLAGS.momentum, nesterov=True)
+    elif FLAGS.optimizer == 'adam':
+        from . import optimizers
+        return optimizers.Adam(learning_rate)
     else:
         raise ValueError('Unknown optimizer {}'.format(FLAGS.optimizer))
 
@@ -172,9 +175,12 @@ class ProjectionHead:
             hiddens_list.append(hiddens)
         return hiddens_list[-1], hiddens_list[FLAGS.ft_proj_selector]
 
-    def backward(self, d_proj_out):
+    def backward(self, d_proj_out, upto=None):
+        """Backward through layers [0, upto) (all of them by default): `upto` = `ft_proj_selector` when the
+        gradient enters at hiddens_list[ft_proj_selector] (finetuning, tf2/model.py:213,267-270)."""
         d = d_proj_out
-        for layer in reversed(self.linear_layers):
+        layers = self.linear_layers if upto is None else self.linear_layers[:upto]
+        for layer in reversed(layers):
             d = layer.backward(d)
         return d
 
@@ -183,13 +189,20 @@ class SupervisedHead:
     """tf2/model.py:216-225."""
 
     def __init__(self, num_classes, vs=None, cin=None, name='head_supervised', **kwargs):
-        self.linear_layer = LinearLayer(vs, name, cin, num_classes, need_dgrad=False)
+        # pretraining: stop_gradient in front of the head (no dgrad); finetuning: the gradient flows on
+        self.need_dx = FLAGS.train_mode == 'finetune'
+        self.linear_layer = LinearLayer(vs, name, cin, num_classes, need_dgrad=self.need_dx)
 
     def __call__(self, inputs, training):
+        e = get_engine()
+        if inputs.dtype != e.act_dtype:       # ft_proj_selector = -1: the fp32 projection output feeds the head
+            c = e.empty(inputs.shape)
+            lib.cast(inputs, e.code(inputs.dtype), c, e.code(c.dtype), inputs.numel(), stream_ptr())
+            inputs = c
         return self.linear_layer(inputs, training, out_dtype=torch.float32)
 
     def backward(self, d_logits):
-        self.linear_layer.backward(d_logits, need_dx=False)
+        return self.linear_layer.backward(d_logits, need_dx=self.need_dx)
 
 
 class Model:
@@ -231,8 +244,6 @@ class Model:
         if inputs.dim() != 4 or inputs.shape[3] is None:
             raise ValueError('The input channels dimension must be statically known '
                              f'(got input shape {tuple(inputs.shape)})')
-        if FLAGS.train_mode == 'finetune':
-            raise NotImplementedError('train_mode=finetune is not on the B200 path yet')
         B, H, W, C6 = inputs.shape
         num_transforms = C6 // 3
         use_blur = bool(FLAGS.use_blur and training and FLAGS.train_mode == 'pretrain')
@@ -245,7 +256,10 @@ class Model:
             hiddens = self.resnet_model(features, training=training, endpoints=endpoints)
             projection_head_outputs, supervised_head_inputs = self._projection_head(hiddens, training)
             supervised_head_outputs = None
-            if FLAGS.train_mode == 'pretrain' and FLAGS.lineareval_while_pretraining:
+            if FLAGS.train_mode == 'finetune':
+                supervised_head_outputs = self.supervised_head(supervised_head_inputs, training)
+                projection_head_outputs = None                          # tf2/model.py:267-270
+            elif FLAGS.train_mode == 'pretrain' and FLAGS.lineareval_while_pretraining:
                 # stop_gradient: nothing flows back from the supervised head (tf2/model.py:272-278)
                 supervised_head_outputs = self.supervised_head(supervised_head_inputs, training)
         finally:
@@ -254,7 +268,18 @@ class Model:
 
     def backward(self, d_projection_head_outputs, d_supervised_head_outputs=None):
         """Explicit `tape.gradient` (tf2/run.py:621): fills `.grad` of every trainable variable."""
+        d_sup_in = None
         if d_supervised_head_outputs is not None:
-            self.supervised_head.backward(d_supervised_head_outputs)
-        d_hiddens = self._projection_head.backward(d_projection_head_outputs)
+            d_sup_in = self.supervised_head.backward(d_supervised_head_outputs)
+        if FLAGS.train_mode == 'finetune':
+            # the loss sees hiddens_list[ft_proj_selector] only: backward through the projection layers below it
+            sel = FLAGS.ft_proj_selector % (FLAGS.num_proj_layers + 1)
+            e = get_engine()
+            if d_sup_in.dtype != (torch.float32 if sel == FLAGS.num_proj_layers else e.act_dtype):
+                c = e.empty(d_sup_in.shape, torch.float32 if sel == FLAGS.num_proj_layers else e.act_dtype)
+                lib.cast(d_sup_in, e.code(d_sup_in.dtype), c, e.code(c.dtype), d_sup_in.numel(), stream_ptr())
+                d_sup_in = c
+            d_hiddens = self._projection_head.backward(d_sup_in, upto=sel)
+        else:
+            d_hiddens = self._projection_head.backward(d_projection_head_outputs)
         self.resnet_model.backward(d_hiddens)

@@ -621,6 +621,13 @@ class Resnet:  # pylint: disable=missing-docstring
         wm = width_multiplier
         self.cifar_stem = cifar_stem
         self.stem_extra = []          # ResNet-D: two more conv+BN pairs after the first
+        # Finetuning with --fine_tune_after_block=k >= 0: the stem and block groups 1..k are `trainable=False`
+        # Keras layers (tf2/resnet.py:548-549,619-692): variables non-trainable, BatchNorm in inference mode,
+        # and a stop_gradient in front of group k+1 (:675-681).
+        ft = FLAGS.fine_tune_after_block if FLAGS.train_mode == 'finetune' else -1
+        self.frozen_groups = max(ft, 0) if ft >= 0 else 0          # number of leading block groups frozen
+        self.stem_frozen = ft >= 0
+        vs.default_trainable = not self.stem_frozen
         if cifar_stem:                                            # :551-564
             self.stem_conv = Conv2dFixedPadding(vs, scope, 3, 64 * wm, 3, 1, stored_cin=self.STEM_CS, need_dgrad=False)
             self.stem_bn = BatchNormRelu(vs, scope, 64 * wm)
@@ -638,15 +645,20 @@ class Resnet:  # pylint: disable=missing-docstring
         self.block_groups = []
         cin = 64 * wm
         for i, (f, s) in enumerate(zip([64, 128, 256, 512], [1, 2, 2, 2])):
+            if self.stem_frozen and ft == i:
+                vs.default_trainable = True
             g = BlockGroup(vs, scope, cin, f * wm, block_fn, layers[i], s, 'block_group%d' % (i + 1))
             self.block_groups.append(g)
             cin = g.cout
+        vs.default_trainable = True
         self.cout = cin
         self.saved = None
 
     def __call__(self, inputs, training, endpoints=None):
         e = get_engine()
         st = stream_ptr()
+        train_all = training
+        training = train_all and not self.stem_frozen          # frozen layers: inference-mode BN, nothing saved
         if endpoints is not None:
             x = self.stem_conv(inputs, training)
             endpoints['initial_conv'] = x
@@ -667,9 +679,10 @@ class Resnet:  # pylint: disable=missing-docstring
         if endpoints is not None:
             endpoints['initial_max_pool'] = x
         for i, g in enumerate(self.block_groups):
-            x = g(x, training)
+            x = g(x, train_all and not (self.stem_frozen and i < self.frozen_groups))
             if endpoints is not None:
                 endpoints['block_group%d' % (i + 1)] = x
+        training = train_all
         N, H, W, C = x.shape
         out = e.empty((N, C))
         lib.global_avgpool_fwd(x, e.code(x.dtype), out, e.code(out.dtype), N, H * W, C, st)   # :693-696
@@ -687,8 +700,12 @@ class Resnet:  # pylint: disable=missing-docstring
         d = e.empty((N, H, W, C))
         lib.global_avgpool_bwd(d_hiddens, e.code(d_hiddens.dtype), d, e.code(d.dtype), N, H * W, C, st)
         d2 = None
-        for g in reversed(self.block_groups):
-            d, d2 = g.backward(d, d2)
+        for i in reversed(range(len(self.block_groups))):
+            if self.stem_frozen and i < self.frozen_groups:
+                return                      # tf.stop_gradient in front of block group `fine_tune_after_block` + 1
+            d, d2 = self.block_groups[i].backward(d, d2)
+        if self.stem_frozen:
+            return
         if pool_saved is not None:
             argmax, (N, H, W, C) = pool_saved
             lib.add_inplace(d, d2, e.code(d.dtype), d.numel(), st)

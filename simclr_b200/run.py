@@ -4,9 +4,12 @@
 `python -m simclr_b200.run --train_batch_size=512 ...` (under torchrun for more
 than one GPU: one process per GPU, NCCL over NVLink) trains on synthetic
 tensors of the reference's input contract (`tf2/data.py:52-62`: [B,H,W,6] fp32 in
-[0,1] + one-hot labels); dataset reading, checkpoints, eval and export of the
-reference driver are outside this path.
+[0,1] + one-hot labels), with the reference's modes (train / eval / train_then_eval,
+pretrain / finetune), checkpoint cadence and TensorBoard metrics; dataset reading (TFDS)
+and SavedModel export are outside this path.
 """
+import json
+import math
 import os
 
 import torch
@@ -82,16 +85,21 @@ class Trainer:
                                                           grad_scale=1.0 / (supervised_head_outputs.shape[0] * R))
             loss = sup_loss if loss is None else loss + sup_loss
             self.metrics['supervised_loss'] = sup_loss
+            self.metrics['supervised_logits'] = supervised_head_outputs
         weight_decay = model_lib.add_weight_decay(model, adjust_per_optimizer=True)
         self.metrics['weight_decay'] = weight_decay
         loss = loss + weight_decay
         self.metrics['total_loss'] = loss
         model.backward(d_proj, d_sup)
-        # d(weight_decay)/dW = wd * W on the supervised-head kernel; loss / R per replica
-        if 'lars' in FLAGS.optimizer:
-            for v in model.trainable_variables:
-                if 'head_supervised' in v.name and 'bias' not in v.name:
-                    lib.axpy(float(FLAGS.weight_decay) / R, v.value, v.grad, v.numel, st)
+        # d(weight_decay)/dW = wd * W (loss / R per replica): with LARS on the supervised-head kernel only (the
+        # optimizer decays the rest), otherwise on every non-BatchNorm variable (tf2/model.py:47-69)
+        for v in model.trainable_variables:
+            if 'lars' in FLAGS.optimizer:
+                decayed = 'head_supervised' in v.name and 'bias' not in v.name
+            else:
+                decayed = 'batch_normalization' not in v.name
+            if decayed and v.grad is not None:
+                lib.axpy(float(FLAGS.weight_decay) / R, v.value, v.grad, v.numel, st)
         return loss
 
     def reduce_gradients(self):
@@ -175,25 +183,153 @@ def synthetic_batch(batch, image_size, num_classes, device, seed):
     return features, labels
 
 
+def synthetic_eval_batch(batch, image_size, num_classes, device, seed):
+    """One view per sample, the contract of the eval / finetune pipeline (tf2/data.py:52-62 with
+    is_pretrain False): [B,H,W,3] fp32 in [0,1] + one-hot labels."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    features = torch.rand(batch, image_size, image_size, 3, device=device, generator=g)
+    idx = torch.randint(0, num_classes, (batch,), device=device, generator=g)
+    return features, torch.nn.functional.one_hot(idx, num_classes).float()
+
+
+def json_serializable(val):
+    try:
+        json.dumps(val)
+        return True
+    except TypeError:
+        return False
+
+
+def perform_evaluation(trainer, eval_steps, ckpt, batch_fn):
+    """tf2/run.py:348-432: restores `ckpt`, runs `eval_steps` inference steps (BatchNorm on moving statistics),
+    accumulates eval/regularization_loss and label top-1 / top-5 accuracy, writes the TensorBoard summaries,
+    result.json, result_<step>.json and flags.json into model_dir.  `batch_fn(i)` -> (features, one-hot labels)."""
+    from . import metrics as metrics_lib, checkpoint as ckpt_lib
+    if FLAGS.train_mode == 'pretrain' and not FLAGS.lineareval_while_pretraining:
+        logging.info('Skipping eval during pretraining without linear eval.')
+        return None
+    model = trainer.model
+    regularization_loss = metrics_lib.Mean('eval/regularization_loss')
+    label_top_1_accuracy = metrics_lib.Accuracy('eval/label_top_1_accuracy')
+    label_top_5_accuracy = metrics_lib.TopKCategoricalAccuracy(5, 'eval/label_top_5_accuracy')
+    all_metrics = [regularization_loss, label_top_1_accuracy, label_top_5_accuracy]
+    global_step = 0
+    if ckpt:
+        logging.info('Restoring from %s', ckpt)
+        global_step = ckpt_lib.CheckpointManager(model, None, FLAGS.model_dir).restore(ckpt)
+        logging.info('Performing eval at step %d', global_step)
+    for i in range(eval_steps):
+        features, labels = batch_fn(i)
+        _, supervised_head_outputs = model(features, training=False)
+        assert supervised_head_outputs is not None
+        metrics_lib.update_finetune_metrics_eval(label_top_1_accuracy, label_top_5_accuracy, supervised_head_outputs, labels)
+        regularization_loss.update_state(model_lib.add_weight_decay(model, adjust_per_optimizer=True))
+        logging.info('Completed eval for %d / %d steps', i + 1, eval_steps)
+    result = {m.name: float(m.result()) for m in all_metrics}
+    result['global_step'] = int(global_step)
+    logging.info(result)
+    if FLAGS.model_dir and trainer.strategy.replica_id == 0:
+        writer = metrics_lib.SummaryWriter(FLAGS.model_dir)
+        metrics_lib.log_and_write_metrics_to_summary(all_metrics, global_step, writer)
+        writer.flush(); writer.close()
+        for name in ('result.json', 'result_%d.json' % result['global_step']):
+            with open(os.path.join(FLAGS.model_dir, name), 'w') as f:
+                json.dump({k: float(v) for k, v in result.items()}, f)
+        with open(os.path.join(FLAGS.model_dir, 'flags.json'), 'w') as f:
+            json.dump({k: v for k, v in FLAGS.flag_values_dict().items() if json_serializable(v)}, f)
+    return result
+
+
 def main(argv):
+    """tf2/run.py:464-664 on synthetic tensors: `--mode=train|eval|train_then_eval`, `--train_mode=pretrain|finetune`,
+    checkpoints every `checkpoint_steps` (resume from the latest one in --model_dir, or weights from --checkpoint),
+    train/* metrics + learning rate flushed to TensorBoard event files at the same cadence.  Reading a dataset
+    (TFDS) and SavedModel export are not part of this path (N1 / N2)."""
+    from . import metrics as metrics_lib, checkpoint as ckpt_lib
     if len(argv) > 1:
         raise app.UsageError('Too many command-line arguments.')
-    if FLAGS.mode != 'train' or FLAGS.train_mode != 'pretrain':
-        raise NotImplementedError('only --mode=train --train_mode=pretrain is on the B200 path')
     rank = init_distributed()
     engine_lib.set_engine(engine_lib.Engine())
     trainer = Trainer()
     R = trainer.strategy.num_replicas_in_sync
-    assert FLAGS.train_batch_size % R == 0
+    dev = trainer.engine.device
+    num_train_examples, num_classes = trainer.num_examples, trainer.num_classes
+    num_eval_examples = FLAGS.b200_num_eval_examples
+    train_steps = model_lib.get_train_steps(num_train_examples)
+    eval_steps = FLAGS.eval_steps or int(math.ceil(num_eval_examples / FLAGS.eval_batch_size))
+    epoch_steps = int(round(num_train_examples / FLAGS.train_batch_size))
+    checkpoint_steps = FLAGS.checkpoint_steps or (FLAGS.checkpoint_epochs * epoch_steps)
+    logging.info('# train examples: %d', num_train_examples)
+    logging.info('# train_steps: %d', train_steps)
+    logging.info('# eval examples: %d', num_eval_examples)
+    logging.info('# eval steps: %d', eval_steps)
+    assert FLAGS.eval_batch_size % R == 0 and FLAGS.train_batch_size % R == 0
+    eval_fn = lambda i: synthetic_eval_batch(FLAGS.eval_batch_size // R, FLAGS.image_size, num_classes, dev, 99991 * (rank + 1) + i)
+
+    if FLAGS.mode == 'eval':
+        manager = ckpt_lib.CheckpointManager(trainer.model, None, FLAGS.model_dir)
+        result = perform_evaluation(trainer, eval_steps, manager.latest_checkpoint, eval_fn)
+        logging.info('Eval complete. Exiting...')
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        return result
+
     B = FLAGS.train_batch_size // R            # per-replica batch size (tf2/data.py:45)
-    features, labels = synthetic_batch(B, FLAGS.image_size, trainer.num_classes, trainer.engine.device, 1234 + rank)
-    train_steps = model_lib.get_train_steps(trainer.num_examples)
-    for step in range(train_steps):
-        loss = trainer.single_step(features, labels)
-        if rank == 0 and (step % 10 == 0 or step == train_steps - 1):
-            logging.info('Step: [%d] total_loss = %f', step, float(loss))
+    pretrain = FLAGS.train_mode == 'pretrain'
+    writer = metrics_lib.SummaryWriter(FLAGS.model_dir) if (FLAGS.model_dir and rank == 0) else None
+    weight_decay_metric = metrics_lib.Mean('train/weight_decay')
+    total_loss_metric = metrics_lib.Mean('train/total_loss')
+    all_metrics = [weight_decay_metric, total_loss_metric]
+    if pretrain:
+        contrast_loss_metric = metrics_lib.Mean('train/contrast_loss')
+        contrast_acc_metric = metrics_lib.Mean('train/contrast_acc')
+        contrast_entropy_metric = metrics_lib.Mean('train/contrast_entropy')
+        all_metrics.extend([contrast_loss_metric, contrast_acc_metric, contrast_entropy_metric])
+    if not pretrain or FLAGS.lineareval_while_pretraining:
+        supervised_loss_metric = metrics_lib.Mean('train/supervised_loss')
+        supervised_acc_metric = metrics_lib.Mean('train/supervised_acc')
+        all_metrics.extend([supervised_loss_metric, supervised_acc_metric])
+    manager = ckpt_lib.try_restore_from_checkpoint(trainer.model, trainer.optimizer) if FLAGS.model_dir else None
+    steps_per_loop = max(1, checkpoint_steps)
+    cur_step = trainer.optimizer.iterations
+    while cur_step < train_steps:
+        for _ in range(min(steps_per_loop, train_steps - cur_step)):
+            seed = 1234 + rank + 7919 * cur_step
+            if pretrain:
+                features, labels = synthetic_batch(B, FLAGS.image_size, num_classes, dev, seed)
+            else:
+                features, labels = synthetic_eval_batch(B, FLAGS.image_size, num_classes, dev, seed)
+            loss = trainer.single_step(features, labels)
+            m = trainer.metrics
+            weight_decay_metric.update_state(m['weight_decay'])
+            total_loss_metric.update_state(m['total_loss'])
+            if pretrain:
+                metrics_lib.update_pretrain_metrics_train(contrast_loss_metric, contrast_acc_metric, contrast_entropy_metric,
+                                                          m['contrast_loss'], m['logits_con'], None,
+                                                          trainer.strategy.replica_id)
+            if 'supervised_loss' in m:
+                metrics_lib.update_finetune_metrics_train(supervised_loss_metric, supervised_acc_metric,
+                                                          m['supervised_loss'], labels, m['supervised_logits'])
+            cur_step = trainer.optimizer.iterations
+        if manager is not None and rank == 0:
+            manager.save(cur_step)
+        logging.info('Completed: %d / %d steps', cur_step, train_steps)
+        if rank == 0:
+            metrics_lib.log_and_write_metrics_to_summary(all_metrics, cur_step, writer)
+            if writer is not None:
+                writer.scalar('learning_rate', trainer.learning_rate(cur_step), cur_step)
+                writer.flush()
+        for metric in all_metrics:
+            metric.reset_states()
+    logging.info('Training complete...')
+    result = None
+    if FLAGS.mode == 'train_then_eval':
+        result = perform_evaluation(trainer, eval_steps, manager.latest_checkpoint if manager else None, eval_fn)
+    if writer is not None:
+        writer.close()
     if dist.is_initialized():
         dist.destroy_process_group()
+    return result
 
 
 if __name__ == '__main__':

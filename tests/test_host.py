@@ -216,3 +216,65 @@ def test_profiles_are_consistent_with_their_sources(tmp_path):
     roof = line['roofline']
     assert roof['traffic'] is not None and 0.9 < roof['traffic'] / roof['algorithmic_bytes'] < 1.1
     assert line['gpu_launches'] > 0 and line['e2e']['h2d_bytes_per_step'] > 0
+
+
+def test_metrics_and_event_file(tmp_path):
+    """tf2/metrics.py stand-ins and the hand-encoded TensorBoard event records."""
+    import struct
+    import torch
+    from simclr_b200 import metrics as M
+    assert M.crc32c(b'123456789') == 0xE3069283                     # CRC-32C check value
+    m = M.Mean('train/x'); m.update_state(1.0); m.update_state(torch.tensor(3.0)); assert m.result() == 2.0
+    m.reset_states(); assert m.result() == 0.0
+    logits = torch.tensor([[0.1, 0.9, 0.0], [0.8, 0.1, 0.1], [0.2, 0.3, 0.5]])
+    labels = torch.nn.functional.one_hot(torch.tensor([1, 2, 2]), 3).float()
+    a1 = M.Accuracy('a1'); a5 = M.TopKCategoricalAccuracy(2, 'a2')
+    M.update_finetune_metrics_eval(a1, a5, logits, labels)
+    assert abs(a1.result() - 2 / 3) < 1e-6 and abs(a5.result() - 2 / 3) < 1e-6
+    sl, sa = M.Mean('l'), M.Mean('a')
+    M.update_finetune_metrics_train(sl, sa, 0.5, labels[:1], torch.cat([logits[:1], logits[:1]]))   # labels doubled
+    assert sa.result() == 1.0
+    w = M.SummaryWriter(str(tmp_path))
+    w.scalar('train/total_loss', 1.5, step=7); w.flush(); w.close()
+    data = open(w.path, 'rb').read()
+    recs, off = [], 0
+    while off < len(data):
+        (n,) = struct.unpack('<Q', data[off:off + 8])
+        assert struct.unpack('<I', data[off + 8:off + 12])[0] == M._masked_crc(data[off:off + 8])
+        body = data[off + 12:off + 12 + n]
+        assert struct.unpack('<I', data[off + 12 + n:off + 16 + n])[0] == M._masked_crc(body)
+        recs.append(body); off += 16 + n
+    assert len(recs) == 2 and b'brain.Event:2' in recs[0]
+    assert b'train/total_loss' in recs[1] and struct.pack('<f', 1.5) in recs[1] and recs[1][9:11] == bytes([0x10, 0x07])   # step = 7
+
+
+def test_checkpoint_manager_roundtrip(tmp_path):
+    """CheckpointManager: reference variable names, pruning to max_to_keep, latest, partial restore."""
+    import torch
+    from simclr_b200 import checkpoint as C
+
+    class V:
+        def __init__(self, name, t): self.name, self.value, self.shape = name, t, tuple(t.shape)
+
+    class FakeModel:
+        def __init__(self):
+            self.variables = [V('resnet/conv2d/kernel:0', torch.arange(6.).view(1, 1, 2, 3)), V('head/bias:0', torch.ones(4))]
+            self.trainable_variables = self.variables
+
+    class FakeOpt:
+        def __init__(self): self._flat_v = torch.full((8,), 2.0); self.iterations = 0
+        def ensure_built(self, vs): pass
+
+    m, o = FakeModel(), FakeOpt()
+    mgr = C.CheckpointManager(m, o, str(tmp_path), max_to_keep=2)
+    assert mgr.latest_checkpoint is None
+    for step in (10, 20, 30):
+        m.variables[1].value.fill_(float(step)); mgr.save(step)
+    assert [os.path.basename(p) for p in mgr._paths()] == ['ckpt-20.npz', 'ckpt-30.npz']
+    m2, o2 = FakeModel(), FakeOpt(); o2._flat_v.zero_()
+    m2.variables.append(V('new/extra:0', torch.zeros(2)))               # not in the file: skipped (expect_partial)
+    step = C.CheckpointManager(m2, o2, str(tmp_path)).restore(mgr.latest_checkpoint)
+    assert step == 30 and o2.iterations == 30 and float(m2.variables[1].value[0]) == 30.0 and float(o2._flat_v[0]) == 2.0
+    m3 = FakeModel(); m3.variables[1].value.zero_()
+    assert C.CheckpointManager(m3, None, str(tmp_path)).restore(mgr.latest_checkpoint, weights_only=True) == 0
+    assert float(m3.variables[1].value[0]) == 30.0
