@@ -157,5 +157,7 @@ def add_weight_decay(cfg, P, adjust_per_optimizer=True):
         l2 = [0.5 * (v ** 2).sum() for n, v in P.items()
               if 'head_supervised' in n and 'bias' not in n]
         return cfg.weight_decay * sum(l2) if l2 else 0
-    l2 = [0.5 * (v ** 2).sum() for n, v in P.items() if 'batch_normalization' not in n]
+    # `model.trainable_weights` (tf2/model.py:64-66): variables of frozen (trainable=False) layers are left out
+    frozen = resnet_lib.frozen_variable_names(cfg, P)
+    l2 = [0.5 * (v ** 2).sum() for n, v in P.items() if 'batch_normalization' not in n and n not in frozen]
     return cfg.weight_decay * sum(l2)

@@ -435,11 +435,8 @@ int simclr_ntxent_forward(const float* z_all, int64_t B, int64_t R, int64_t D, i
   int tps;
   const int splits = pick_splits(B, R, &tps);
   const size_t smem = (size_t)(RB + CT) * (D + 1) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SIMCLR_CHECK_CUDA(cudaFuncSetAttribute(fwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (RB + CT) * (MAXD + 1) * 4));
-    attr_set = true;
-  }
+  // a per-device attribute: set on every call (a process may drive more than one GPU)
+  SIMCLR_CHECK_CUDA(cudaFuncSetAttribute(fwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (RB + CT) * (MAXD + 1) * 4));
   float* part = (float*)workspace;
   dim3 grid((unsigned)((2 * B + RB - 1) / RB), splits);
   fwd_partial_kernel<<<grid, NT, smem, st>>>(z_all, B, R, (int)D, replica_id, 1.f / temperature, logits_ab, part, tps);
@@ -477,12 +474,8 @@ int simclr_ntxent_backward(const float* z_all, const float* lse_all, const float
   int tps;
   const int splits = pick_splits(B, R, &tps);
   const size_t smem = ((size_t)(RB + CT) * (D + 1) + RB * CT + CT) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SIMCLR_CHECK_CUDA(cudaFuncSetAttribute(bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           ((RB + CT) * (MAXD + 1) + RB * CT + CT) * 4));
-    attr_set = true;
-  }
+  SIMCLR_CHECK_CUDA(cudaFuncSetAttribute(bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ((RB + CT) * (MAXD + 1) + RB * CT + CT) * 4));
   float* part = (float*)workspace;
   dim3 grid((unsigned)((2 * B + RB - 1) / RB), splits);
   bwd_partial_kernel<<<grid, NT, smem, st>>>(z_all, lse_all, B, R, (int)D, replica_id, 1.f / temperature, part, tps);

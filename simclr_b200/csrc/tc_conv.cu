@@ -35,6 +35,21 @@ template <int BN> struct Tile {
   static constexpr size_t SMEM_BYTES = 1024 /*align*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
 };
 
+// wgrad work item: MT x 128 k-rows (MT accumulators sharing every dY tile).  MT = 2 halves the dY bytes that
+// cross L2 -> SM per MMA (wide layers are bound by that traffic, not by the tensor pipe); its 2 x BN fp32
+// accumulator columns fill TMEM for BN = 256, so the accumulators are single-buffered (items are long
+// pixel loops: the un-overlapped epilogue is a few percent).
+template <int BN, int MT> struct WTile {
+  static constexpr int A_BYTES = MT * A_STAGE_BYTES;
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = PIPE_BYTES / STAGE_BYTES;
+  static constexpr int NACC = MT == 1 ? 2 : 1;                       // accumulator sets in flight
+  static constexpr int TMEM_COLS = NACC * MT * BN < 32 ? 32 : NACC * MT * BN;
+  static constexpr int GATHER_DEPTH = STAGES > 4 ? 4 : STAGES - 1;
+  static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 2 * A_STAGE_BYTES + 256;
+};
+
 struct Geom {
   const void* src;     // gathered tensor: X (fprop/wgrad) or dY (dgrad), NHWC
   void* out;
@@ -59,6 +74,7 @@ struct Geom {
   // TMA im2col feed of the gathered operand: base pixel of GEMM row (n, p, q) is
   // (q*stride + im_base, p*stride + im_base); the tap goes into the instruction's filter offsets
   int im2col, im_base, im_nimg;
+  int wg_mt;           // wgrad: 128-row k tiles per work item (1 or 2)
   int accum;           // fp32 outputs only: add into `out` (TMA reduce-add / atomics) instead of storing (tc3 passes)
 };
 
@@ -577,12 +593,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 // A^T (activations) and B (dY) are both MN-major: the reduction runs over pixels.
 // Work item = (128 k-rows) x (BN couts) x (pixel split); fp32 atomics combine splits.
 // ===========================================================================
-template <typename T, int BN, bool SMALLC, bool A_TMA, bool TMA_RED>
+template <typename T, int BN, bool SMALLC, bool A_TMA, bool TMA_RED, int MT = 1>
 __global__ void __launch_bounds__(wgrad_threads(A_TMA), 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
              const __grid_constant__ CUtensorMap tmap_dw, const Geom g, float* __restrict__ dw) {
-  using TL = Tile<BN>;
+  using TL = WTile<BN, MT>;
   constexpr int STAGES = TL::STAGES;
+  constexpr int NACC = TL::NACC;
+  static_assert(MT == 1 || (A_TMA && TMA_RED && !SMALLC), "256-row tiles: TMA-fed, reduce-add epilogue only");
   constexpr bool TF32 = Elt<T>::TF32;
   constexpr int ATOM_E = Elt<T>::KBE;            // elements along MN per 128-byte atom row
   constexpr int CH = Elt<T>::CH;
@@ -633,12 +651,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
       if (kb0 >= kb1) continue;
       mbar_wait(&ctl.tmem_full[as], aphase, 50);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(warp * 32) << 16);
+      const uint32_t tbase = tmem_base + (uint32_t)(as * MT * BN) + ((uint32_t)(warp * 32) << 16);
       if (TMA_RED) {
         // partial tile -> swizzled smem [128 k-rows][32 fp32] -> TMA reduce-add into dW (splits combine at L2)
         const int row = warp * 32 + lane;
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc, ++box_ctr) {
+        for (int cm = 0; cm < MT * (BN / 32); ++cm, ++box_ctr) {
+          const int mt = cm / (BN / 32), cc = cm - mt * (BN / 32);
           uint8_t* stage = ctl.epi + (box_ctr & 1) * A_STAGE_BYTES;
           const int n0 = tn * BN + cc * 32;
           const bool live = n0 < g.Cout;
@@ -647,9 +666,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
             named_barrier_sync(1, EPI_THREADS);
           }
           uint32_t acc[32];
-          tmem_ld32(tbase + cc * 32, acc);
+          tmem_ld32(tbase + mt * BN + cc * 32, acc);
           tmem_ld_wait();
-          if (cc == BN / 32 - 1) { tc_fence_before(); warp_arrive(&ctl.tmem_empty[as]); }
+          if (cm == MT * (BN / 32) - 1) { tc_fence_before(); warp_arrive(&ctl.tmem_empty[as]); }
           if (live) {
             const uint32_t srow = smem_u32(stage);
 #pragma unroll
@@ -657,7 +676,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
               sts16(srow + sw128_offset(row, q), make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
             fence_proxy_async();
             named_barrier_sync(1, EPI_THREADS);
-            if (threadIdx.x == 0) { tma_reduce_add_2d(&tmap_dw, stage, n0, tk * 128); tma_store_commit(); }
+            if (threadIdx.x == 0) { tma_reduce_add_2d(&tmap_dw, stage, n0, (tk * MT + mt) * 128); tma_store_commit(); }
           }
         }
       } else {
@@ -688,7 +707,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         tc_fence_before();
         warp_arrive(&ctl.tmem_empty[as]);
       }
-      as ^= 1; if (as == 0) aphase ^= 1;
+      if (++as == NACC) { as = 0; aphase ^= 1; }
     }
     if (TMA_RED && threadIdx.x == 0) tma_store_wait_all<0>();
   } else if (warp == 4) {
@@ -704,24 +723,26 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
       if (kb0 >= kb1) continue;
       mbar_wait(&ctl.tmem_empty[as], aphase ^ 1, 60);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_u + (uint32_t)(as * BN);
+      const uint32_t d_tmem = tmem_u + (uint32_t)(as * MT * BN);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&ctl.full[pp.stage], pp.phase, 61);
         tc_fence_after();
         const uint32_t a_lo = smem_lo + (uint32_t)pp.stage * (TL::STAGE_BYTES >> 4);
-        const uint32_t b_lo = a_lo + (A_STAGE_BYTES >> 4);
+        const uint32_t b_lo = a_lo + (TL::A_BYTES >> 4);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma<TF32>(d_tmem, desc_pack(a_lo + k * (UMMA_K * 128 >> 4), HI), desc_pack(b_lo + k * (UMMA_K * 128 >> 4), HI), IDESC,
-                       (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma<TF32>(d_tmem + mt * BN, desc_pack(a_lo + mt * (A_STAGE_BYTES >> 4) + k * (UMMA_K * 128 >> 4), HI),
+                         desc_pack(b_lo + k * (UMMA_K * 128 >> 4), HI), IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&ctl.empty[pp.stage]);
           if (kb == kb1 - 1) umma_commit(&ctl.tmem_full[as]);
         }
         __syncwarp();
         advance<STAGES>(pp);
       }
-      as ^= 1; if (as == 0) aphase ^= 1;
+      if (++as == NACC) { as = 0; aphase ^= 1; }
     }
   } else if (warp == 5) {
     if (lane == 0) {
@@ -731,17 +752,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&ctl.empty[pp.stage], pp.phase ^ 1, 70);
           uint8_t* a_dst = smem + (size_t)pp.stage * TL::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&ctl.full[pp.stage], TL::B_STAGE_BYTES + (A_TMA ? A_STAGE_BYTES : 0));
+          uint8_t* b_dst = a_dst + TL::A_BYTES;
+          mbar_arrive_expect_tx(&ctl.full[pp.stage], TL::B_STAGE_BYTES + (A_TMA ? TL::A_BYTES : 0));
           if (A_TMA) {
             if (g.im2col) {  // one im2col column of PXS pixels per atom: the atom's tap is the filter offset
               uint32_t n, rem, p, q;
               g.dPQ.divmod((uint32_t)(kb * PXS), n, rem);
               g.dQ.divmod(rem, p, q);
 #pragma unroll
-              for (int a = 0; a < A_ATOMS; ++a) {
+              for (int a = 0; a < MT * A_ATOMS; ++a) {
                 uint32_t tap, c, r, s2;
-                g.dC.divmod((uint32_t)(tk * 128 + a * ATOM_E), tap, c);
+                g.dC.divmod((uint32_t)(tk * MT * 128 + a * ATOM_E), tap, c);
                 g.dS.divmod(tap, r, s2);
                 const bool live = (int)tap < g.RS;     // k-rows past R*S*C: read a non-existent image (zeros)
                 tma_load_im2col(a_dst + a * ATOM_BYTES, &tmap_x, &ctl.full[pp.stage], (int)c,
@@ -750,8 +771,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
               }
             } else {         // 1x1 stride-1: the activation tile is a plain [pixels][channels] box
 #pragma unroll
-              for (int a = 0; a < A_ATOMS; ++a)
-                tma_load_2d(a_dst + a * ATOM_BYTES, &tmap_x, &ctl.full[pp.stage], tk * 128 + a * ATOM_E, kb * PXS);
+              for (int a = 0; a < MT * A_ATOMS; ++a)
+                tma_load_2d(a_dst + a * ATOM_BYTES, &tmap_x, &ctl.full[pp.stage], tk * MT * 128 + a * ATOM_E, kb * PXS);
             }
           }
 #pragma unroll
@@ -874,8 +895,7 @@ template <typename T, typename To, int BN, bool A_TMA, bool SMALLC, bool TMA_EPI
 int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const Geom& g, double* bn_sums,
                  cudaStream_t st) {
   auto kern = igemm_kernel<T, To, BN, A_TMA, SMALLC, TMA_EPI, STATS>;
-  static bool attr = false;
-  if (!attr) { int rc = set_smem_attr(kern, Tile<BN>::SMEM_BYTES); if (rc) return rc; attr = true; }
+  { int rc = set_smem_attr(kern, Tile<BN>::SMEM_BYTES); if (rc) return rc; }   // a per-DEVICE attribute: set on every launch
   int grid = g.tiles_m * g.tiles_n; if (grid > num_sms()) grid = num_sms();
   if (STATS) {                 // one column block per CTA: tile = blockIdx.x + i*gridDim.x keeps tn fixed
     grid = grid / g.tiles_n * g.tiles_n;
@@ -1119,14 +1139,13 @@ int run_dgrad_strided(const void* dy, const void* wd, void* dx, int dtype, int o
   return SIMCLR_OK;
 }
 
-template <typename T, int BN, bool SMALLC, bool A_TMA, bool TMA_RED>
+template <typename T, int BN, bool SMALLC, bool A_TMA, bool TMA_RED, int MT = 1>
 int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, const CUtensorMap& tdw, const Geom& g, float* dw,
                  cudaStream_t st) {
-  auto kern = wgrad_kernel<T, BN, SMALLC, A_TMA, TMA_RED>;
-  static bool attr = false;
-  if (!attr) { int rc = set_smem_attr(kern, Tile<BN>::SMEM_BYTES); if (rc) return rc; attr = true; }
+  auto kern = wgrad_kernel<T, BN, SMALLC, A_TMA, TMA_RED, MT>;
+  int rc = set_smem_attr(kern, WTile<BN, MT>::SMEM_BYTES); if (rc) return rc;      // per device: set every time
   int grid = g.tiles_m * g.tiles_n * g.splits; if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, wgrad_threads(A_TMA), Tile<BN>::SMEM_BYTES, st>>>(tx, tdy, tdw, g, dw);
+  kern<<<grid, wgrad_threads(A_TMA), WTile<BN, MT>::SMEM_BYTES, st>>>(tx, tdy, tdw, g, dw);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
@@ -1135,6 +1154,7 @@ int dispatch_wgrad2(bool smallc, bool a_tma, bool tma_red, const CUtensorMap& tx
                     const CUtensorMap& tdw, const Geom& g, float* dw, cudaStream_t st) {
   if (smallc) return launch_wgrad<T, BN, true, false, false>(tx, tdy, tdw, g, dw, st);
   if (tma_red) {
+    if (a_tma && g.wg_mt == 2) return launch_wgrad<T, BN, false, true, true, 2>(tx, tdy, tdw, g, dw, st);
     if (a_tma) return launch_wgrad<T, BN, false, true, true>(tx, tdy, tdw, g, dw, st);
     return launch_wgrad<T, BN, false, false, true>(tx, tdy, tdw, g, dw, st);
   }
@@ -1231,7 +1251,7 @@ static int wgrad_tc_impl(const void* x, const void* dy, float* dw, int dtype, in
   g.M = M; g.n_out = (int)Cout; g.ldc = (int)Cout;
   g.num_kb = (int)((M + pxs - 1) / pxs);
   g.tiles_m = (int)((R * Sk * Cs + 127) / 128); g.tiles_n = (int)((Cout + bn - 1) / bn);
-  g.Cin = (int)Cin; g.Cout = (int)Cout;
+  g.Cin = (int)Cin; g.Cout = (int)Cout; g.wg_mt = 1;
   g.use_tab = 0; g.cblocks = 1; g.os = 0; g.oh0 = g.ow0 = 0; g.OH = g.OW = 0; g.tap_sign = 1; g.accum = 0;
   const int tiles = g.tiles_m * g.tiles_n;
   int splits = (2 * num_sms() + tiles - 1) / tiles;
@@ -1258,6 +1278,24 @@ static int wgrad_tc_impl(const void* x, const void* dy, float* dw, int dtype, in
   // splits are combined by TMA reduce-add when dW is a plain [R*S*Cin][Cout] fp32 matrix with 16-byte rows
   CUtensorMap tdw;
   const bool tma_red = !stem && Cs == Cin && aligned16(dw) && (Cout * 4) % 16 == 0;
+  // 256-row work items (two accumulators per dY tile) when the filter matrix has whole 256-row tiles or is tall
+  // enough for the padding of the last one not to matter; SIMCLR_TC_WGRAD_MT=1 restores 128-row items (A/B runs)
+  {
+    static int mt_en = -1;
+    if (mt_en < 0) { const char* e = getenv("SIMCLR_TC_WGRAD_MT"); mt_en = (e && e[0] == '1') ? 0 : 1; }
+    const int64_t krows = R * Sk * Cs;
+    if (mt_en && a_tma && tma_red && !smallc && krows >= 256 && (krows % 256 == 0 || krows >= 1024)) {
+      g.wg_mt = 2;
+      g.tiles_m = (int)((krows + 255) / 256);
+      const int tiles2 = g.tiles_m * g.tiles_n;
+      int sp = (2 * num_sms() + tiles2 - 1) / tiles2;
+      const int max_sp = g.num_kb / 8 > 0 ? g.num_kb / 8 : 1;
+      if (sp > max_sp) sp = max_sp;
+      if (sp < 1) sp = 1;
+      g.kb_per_split = (g.num_kb + sp - 1) / sp;
+      g.splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;
+    }
+  }
   if (tma_red) { rc = make_tmap_2d(&tdw, dw, 4, (uint64_t)(R * S * Cin), (uint64_t)Cout, (uint64_t)Cout * 4, 128, 32); if (rc) return rc; }
   else tdw = tdy;
   if (zero && !accumulate_prezeroed()) SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(R * S * Cin * Cout) * sizeof(float), st));

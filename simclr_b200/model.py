@@ -233,6 +233,12 @@ class Model:
     def set_blur_draws(self, sigma, selector):
         """Injects the `tf.random` draws of `batch_random_blur` (tf2/data_util.py:407,425):
         sigma [T] floats, selector [T][B] in {0,1}.  None -> drawn on device."""
+        e = get_engine()       # on the device now: no host-to-device copy inside the step (CUDA-graph capture)
+        if sigma is None:
+            self._blur_draws = None
+            return
+        sigma = torch.as_tensor(sigma, dtype=torch.float32).to(e.device)
+        selector = torch.as_tensor(selector).to(torch.uint8).to(e.device)
         self._blur_draws = (sigma, selector)
 
     def __call__(self, inputs, training, endpoints=None):
