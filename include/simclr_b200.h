@@ -188,6 +188,26 @@ SIMCLR_API int simclr_bn_bwd_apply_coef(const void* dz, int dtype, const void* y
                                         int dy_dtype, int64_t rows, int64_t C, const float* coef,
                                         const float* mask_scale, const float* mask_shift, void* stream);
 
+/* The stem's BatchNorm + ReLU + MaxPooling2D (tf2/resnet.py:593-611) without materialising the BN output:
+ * forward pools relu(scale*y + shift) of the conv output y directly (same rounding as the unfused chain);
+ * backward forms dz = maxpool_bwd(d [+ d2]) * [scale*y + shift > 0] on the fly, first for the BatchNorm
+ * reduction (sums [2][C] = (sum dz, sum dz*xhat)), then for dy = coef0*dz + coef1*y + coef2.
+ * C/8 (bf16; C/4 fp32) must divide 256. */
+SIMCLR_API int simclr_bn_relu_maxpool_fwd(const void* y, int dtype, const float* scale, const float* shift,
+                                          void* out, uint8_t* argmax, int64_t N, int64_t H, int64_t W, int64_t C,
+                                          void* stream);
+SIMCLR_API int simclr_maxpool_bn_bwd_reduce(const void* d, const void* d2, const uint8_t* argmax, const void* y,
+                                            int dtype, int64_t N, int64_t H, int64_t W, int64_t C,
+                                            const float* mean, const float* rstd, const float* scale,
+                                            const float* shift, double* sums, void* stream);
+SIMCLR_API int simclr_maxpool_bn_bwd_apply(const void* d, const void* d2, const uint8_t* argmax, const void* y,
+                                           int dtype, void* dy, int64_t N, int64_t H, int64_t W, int64_t C,
+                                           const float* coef, const float* scale, const float* shift, void* stream);
+/* coef [3][C] of dy = coef0*dz + coef1*y + coef2 (+ dgamma, dbeta from sums_local) alone: the first launch of
+ * simclr_bn_bwd_apply. */
+SIMCLR_API int simclr_bn_bwd_coef(const float* mean, const float* rstd, const float* gamma, const double* sums,
+                                  const double* sums_local, double count, float* coef, float* dgamma,
+                                  float* dbeta, int64_t C, void* stream);
 /* ------------------------------------------------------------------------- *
  * Pooling  (tf2/resnet.py:605-611 MaxPooling2D(3,2,'SAME'); :693-696 mean)
  * ------------------------------------------------------------------------- */

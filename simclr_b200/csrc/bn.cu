@@ -574,6 +574,16 @@ int simclr_bn_bwd_apply(const void* dz, int dtype, const void* y, int y_dtype, v
   return launch_bwd_apply(dz, dtype, y, y_dtype, dy, dy_dtype, rows, C, coef_ws, mask_scale, mask_shift, st);
 }
 
+int simclr_bn_bwd_coef(const float* mean, const float* rstd, const float* gamma, const double* sums,
+                       const double* sums_local, double count, float* coef, float* dgamma, float* dbeta, int64_t C,
+                       void* stream) {
+  SIMCLR_CHECK_ARG(mean && rstd && sums && sums_local && coef && C > 0 && count > 0, "bn_bwd_coef: bad arguments");
+  bn_bwd_coef_kernel<<<(unsigned)((C + 127) / 128), 128, 0, (cudaStream_t)stream>>>(mean, rstd, gamma, sums, sums_local,
+                                                                                   1.0 / count, coef, dgamma, dbeta, (int)C);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
 int simclr_bn_bwd_apply_coef(const void* dz, int dtype, const void* y, int y_dtype, void* dy, int dy_dtype,
                              int64_t rows, int64_t C, const float* coef, const float* mask_scale,
                              const float* mask_shift, void* stream) {

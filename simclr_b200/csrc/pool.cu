@@ -5,15 +5,24 @@
 namespace simclr {
 namespace {
 
-template <typename T>
+// BNRELU: x is the conv output; relu(scale*x + shift), rounded to T exactly like the BatchNorm apply kernel would have
+// stored it, is what the window maximum is taken over -- the stem's BN+ReLU output is never materialised
+// (tf2/resnet.py:593-611: conv -> BatchNormRelu -> MaxPooling2D).
+template <typename T, bool BNRELU>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ argmax, int64_t total,
-                   int H, int W, int C, int Ho, int Wo, int pb_h, int pb_w) {
+                   int H, int W, int C, int Ho, int Wo, int pb_h, int pb_w, const float* __restrict__ scale,
+                   const float* __restrict__ shift) {
   constexpr int V = Vec16<T>::N;
   const int cv = C / V;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % cv) * V;
+    float sc[V], sh[V];
+    if (BNRELU) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) { sc[i] = scale[c + i]; sh[i] = shift[c + i]; }
+    }
     int64_t p = idx / cv;
     const int wo = (int)(p % Wo); p /= Wo;
     const int ho = (int)(p % Ho);
@@ -32,6 +41,10 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restri
         if (w < 0 || w >= W) continue;
         Vec16<T> v; v.load(x + (((n * H + h) * W + w) * (int64_t)C + c));
         float f[V]; v.unpack(f);
+        if (BNRELU) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) f[i] = to_f<T>(from_f<T>(fmaxf(fmaf(f[i], sc[i], sh[i]), 0.f)));
+        }
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           // first maximum in window scan order wins (matches TF / torch argmax routing)
@@ -127,6 +140,117 @@ maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ argmax,
   }
 }
 
+// MaxPooling2D backward fused with the backward pass of the BatchNorm + ReLU in front of it: the gradient w.r.t.
+// the BN output, dz = maxpool_bwd(d [+ d2]) * [scale*y + shift > 0], is formed on the fly from the pooled-size
+// gradient(s), the argmax codes and the conv output y, and never written.  PHASE 0 accumulates the BatchNorm
+// reduction (sum dz, sum dz*(y - mean)) * rstd into `sums` [2][C]; PHASE 1 writes dy = k1*dz + k2*y + k3.
+// Roundings are those of the unfused chain (bf16 sum d + d2, bf16 dz).  Thread -> channel block is fixed
+// (gridDim*256 is a multiple of C/V), so PHASE 0 keeps per-thread partial sums in registers.
+template <typename T, int PHASE>
+__global__ void __launch_bounds__(256)
+maxpool_bn_bwd_kernel(const T* __restrict__ d, const T* __restrict__ d2, const uint8_t* __restrict__ argmax,
+                      const T* __restrict__ y, T* __restrict__ dy_out, int64_t total, int H, int W, int C, int Ho, int Wo,
+                      int pb_h, int pb_w, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
+                      double* __restrict__ sums) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  const int Hb = (H + 1) / 2, Wb = (W + 1) / 2;
+  const int c = (int)((blockIdx.x * 256 + threadIdx.x) % cv) * V;       // fixed for the whole grid-stride loop
+  float sc[V], sh[V], mu[V], k1[V], k2[V], k3[V], s0[V], s1[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sc[i] = scale[c + i]; sh[i] = shift[c + i]; s0[i] = 0.f; s1[i] = 0.f;
+    if (PHASE == 0) mu[i] = mean[c + i];
+    else { k1[i] = coef[c + i]; k2[i] = coef[C + c + i]; k3[i] = coef[2 * C + c + i]; }
+  }
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = idx / cv;
+    const int wb = (int)(p % Wb); p /= Wb;
+    const int hb = (int)(p % Hb);
+    const int64_t n = p / Hb;
+    float g[2][2][V];
+    uint64_t am[2][2];
+    bool live[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int ho = hb - 1 + pb_h + i, wo = wb - 1 + pb_w + j;
+        live[i][j] = ho >= 0 && ho < Ho && wo >= 0 && wo < Wo;
+        am[i][j] = 0;
+        if (live[i][j]) {
+          const int64_t ooff = ((n * Ho + ho) * Wo + wo) * (int64_t)C + c;
+          Vec16<T> v; v.load(d + ooff); v.unpack(g[i][j]);
+          if (d2 != nullptr) {
+            Vec16<T> v2; v2.load(d2 + ooff); float g2[V]; v2.unpack(g2);
+#pragma unroll
+            for (int k = 0; k < V; ++k) g[i][j][k] = to_f<T>(from_f<T>(g[i][j][k] + g2[k]));
+          }
+          if (V == 8) am[i][j] = *reinterpret_cast<const uint64_t*>(argmax + ooff);
+          else am[i][j] = *reinterpret_cast<const uint32_t*>(argmax + ooff);
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) g[i][j][k] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int h = 2 * hb + a;
+      if (h >= H) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int w = 2 * wb + b;
+        if (w >= W) continue;
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int dh = a + 2 - pb_h - 2 * i;
+          if (dh < 0 || dh > 2) continue;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int dw = b + 2 - pb_w - 2 * j;
+            if (dw < 0 || dw > 2 || !live[i][j]) continue;
+            const int code = dh * 3 + dw;
+#pragma unroll
+            for (int k = 0; k < V; ++k) if ((int)((am[i][j] >> (8 * k)) & 0xff) == code) acc[k] += g[i][j][k];
+          }
+        }
+        const int64_t off = ((n * H + h) * W + w) * (int64_t)C + c;
+        Vec16<T> vy; vy.load(y + off); float yy[V]; vy.unpack(yy);
+        float o[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float dz = fmaf(yy[k], sc[k], sh[k]) > 0.f ? to_f<T>(from_f<T>(acc[k])) : 0.f;
+          if (PHASE == 0) { s0[k] += dz; s1[k] = fmaf(dz, yy[k] - mu[k], s1[k]); }
+          else o[k] = fmaf(k1[k], dz, fmaf(k2[k], yy[k], k3[k]));
+        }
+        if (PHASE == 1) { Vec16<T> vo; vo.pack(o); vo.store(dy_out + off); }
+      }
+    }
+  }
+  if (PHASE == 0) {
+    // threads t and t' with t % cv == t' % cv hold partial sums of the same channels: fold in shared memory,
+    // then one fp64 atomic per channel per block
+    __shared__ float sh_s[256][2 * V + 1];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { sh_s[threadIdx.x][k] = s0[k]; sh_s[threadIdx.x][V + k] = s1[k]; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < cv * 2 * V; e += 256) {
+      const int j = e / (2 * V), q = e % (2 * V);
+      double t = 0.0;
+      for (int r = j; r < 256; r += cv) t += (double)sh_s[r][q];
+      const int ch = j * V + (q % V);
+      if (q < V) atomicAdd(&sums[ch], t);
+      else atomicAdd(&sums[C + ch], t * (double)rstd[ch]);
+    }
+  }
+}
+
 // x [N][HW][C] -> y [N][C] mean.  One thread per (n, channel); HW strided reads are
 // coalesced across channels.
 template <typename T, typename To>
@@ -182,10 +306,10 @@ int simclr_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, int dtype, 
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SIMCLR_F32) {
     const int64_t total = N * Ho * Wo * (C / 4);
-    maxpool_fwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, argmax, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw);
+    maxpool_fwd_kernel<float, false><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, argmax, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw, nullptr, nullptr);
   } else if (dtype == SIMCLR_BF16) {
     const int64_t total = N * Ho * Wo * (C / 8);
-    maxpool_fwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, argmax, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw);
+    maxpool_fwd_kernel<bf16, false><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, argmax, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw, nullptr, nullptr);
   } else { set_error("maxpool_fwd: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
@@ -207,6 +331,62 @@ int simclr_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int
   } else { set_error("maxpool_bwd: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
+}
+
+int simclr_bn_relu_maxpool_fwd(const void* y, int dtype, const float* scale, const float* shift, void* out,
+                               uint8_t* argmax, int64_t N, int64_t H, int64_t W, int64_t C, void* stream) {
+  SIMCLR_CHECK_ARG(y && scale && shift && out && argmax, "bn_relu_maxpool_fwd: null pointer");
+  SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bn_relu_maxpool_fwd: need C%%8==0 and positive dims");
+  int64_t Ho, Wo; int pbh, pbw;
+  same_pad(H, &Ho, &pbh); same_pad(W, &Wo, &pbw);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SIMCLR_F32) {
+    const int64_t total = N * Ho * Wo * (C / 4);
+    maxpool_fwd_kernel<float, true><<<grid_for(total, 256), 256, 0, st>>>((const float*)y, (float*)out, argmax, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw, scale, shift);
+  } else if (dtype == SIMCLR_BF16) {
+    const int64_t total = N * Ho * Wo * (C / 8);
+    maxpool_fwd_kernel<bf16, true><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)y, (bf16*)out, argmax, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw, scale, shift);
+  } else { set_error("bn_relu_maxpool_fwd: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+static int maxpool_bn_bwd(int phase, const void* d, const void* d2, const uint8_t* argmax, const void* y, int dtype,
+                          void* dy, int64_t N, int64_t H, int64_t W, int64_t C, const float* mean, const float* rstd,
+                          const float* scale, const float* shift, const float* coef, double* sums, void* stream) {
+  const int V = dtype == SIMCLR_BF16 ? 8 : 4;
+  const int64_t cv = C / V;
+  SIMCLR_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && 256 % cv == 0,
+                   "maxpool_bn_bwd: need C%%8==0 and C/%d dividing 256 (C=%lld)", V, (long long)C);
+  int64_t Ho, Wo; int pbh, pbw;
+  same_pad(H, &Ho, &pbh); same_pad(W, &Wo, &pbw);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = N * ((H + 1) / 2) * ((W + 1) / 2) * cv;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * (phase == 0 ? 4 : 16);       // phase 0 ends with one atomic per channel per block
+  if (blocks > cap) blocks = cap;
+  if (phase == 0 && !accumulate_prezeroed()) SIMCLR_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
+#define MPB(T, PH) maxpool_bn_bwd_kernel<T, PH><<<(unsigned)blocks, 256, 0, st>>>((const T*)d, (const T*)d2, argmax, (const T*)y, (T*)dy, total, (int)H, (int)W, (int)C, (int)Ho, (int)Wo, pbh, pbw, mean, rstd, scale, shift, coef, sums)
+  if (dtype == SIMCLR_F32) { if (phase == 0) MPB(float, 0); else MPB(float, 1); }
+  else if (dtype == SIMCLR_BF16) { if (phase == 0) MPB(bf16, 0); else MPB(bf16, 1); }
+  else { set_error("maxpool_bn_bwd: unknown dtype"); return SIMCLR_ERR_INVALID_ARG; }
+#undef MPB
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_maxpool_bn_bwd_reduce(const void* d, const void* d2, const uint8_t* argmax, const void* y, int dtype,
+                                 int64_t N, int64_t H, int64_t W, int64_t C, const float* mean, const float* rstd,
+                                 const float* scale, const float* shift, double* sums, void* stream) {
+  SIMCLR_CHECK_ARG(d && argmax && y && mean && rstd && scale && shift && sums, "maxpool_bn_bwd_reduce: null pointer");
+  return maxpool_bn_bwd(0, d, d2, argmax, y, dtype, nullptr, N, H, W, C, mean, rstd, scale, shift, nullptr, sums, stream);
+}
+
+int simclr_maxpool_bn_bwd_apply(const void* d, const void* d2, const uint8_t* argmax, const void* y, int dtype, void* dy,
+                                int64_t N, int64_t H, int64_t W, int64_t C, const float* coef, const float* scale,
+                                const float* shift, void* stream) {
+  SIMCLR_CHECK_ARG(d && argmax && y && dy && coef && scale && shift, "maxpool_bn_bwd_apply: null pointer");
+  return maxpool_bn_bwd(1, d, d2, argmax, y, dtype, dy, N, H, W, C, nullptr, nullptr, scale, shift, coef, nullptr, stream);
 }
 
 int simclr_global_avgpool_fwd(const void* x, int dtype, void* y, int y_dtype, int64_t N, int64_t HW, int64_t C,

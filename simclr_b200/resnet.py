@@ -33,12 +33,11 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
         self.moving_variance = vs.add(pre + '/moving_variance:0', (channels,), 'ones', trainable=False)
         self.saved = None
 
-    def __call__(self, inputs, training, residual=None, relu=None, out_dtype=None, sums=None):
-        """`sums`: [2C] fp64 sum / sum of squares already produced by the conv epilogue."""
+    def _statistics(self, y, training, sums=None):
+        """(mean, rstd, scale, shift) of this call: batch statistics (SyncBN: global, exchanged over peer memory or
+        NCCL) with the moving-average update when training, the moving statistics otherwise."""
         e = get_engine()
-        relu = self.relu if relu is None else relu
         C = self.C
-        y = inputs
         rows = y.numel() // C
         st = stream_ptr()
         stats = e.empty((4, C), torch.float32)     # mean, rstd, scale, shift
@@ -66,6 +65,71 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
             sc = r if g is None else g * r
             mean.copy_(self.moving_mean.value); rstd.copy_(r); scale.copy_(sc)
             shift.copy_(-self.moving_mean.value * sc if b is None else b - self.moving_mean.value * sc)
+        return mean, rstd, scale, shift
+
+    def _coefficients(self, sums, rows, mean, rstd):
+        """coef [3][C] of dy = k1*dz + k2*y + k3 from the (global) backward sums; fills dgamma / dbeta."""
+        e = get_engine()
+        C = self.C
+        coef = e.empty((3 * C,), torch.float32)
+        gam = None if self.gamma is None else self.gamma.value
+        dgam = None if self.gamma is None else self.gamma.grad
+        dbet = None if self.beta is None else self.beta.grad
+        count = float(rows)
+        if e.sync_bn and e.ctx.comm is not None and 2 * C * 8 <= e.ctx.comm.slot_bytes:
+            e.ctx.comm.bn_bwd_coef(sums, count, mean, rstd, gam, coef, dgam, dbet, C)
+        else:
+            sums_g = sums
+            if e.sync_bn:
+                sums_g = sums.clone()
+                e.ctx.all_reduce_sum(sums_g)
+                count *= e.ctx.num_replicas_in_sync
+            lib.bn_bwd_coef(mean, rstd, gam, sums_g, sums, count, coef, dgam, dbet, C, stream_ptr())
+        return coef
+
+    # -- stem: BN + ReLU + MaxPooling2D(3, 2, 'SAME') without materialising the BN output -----------------
+    def forward_maxpool(self, y, sums=None):
+        """Training forward of `BatchNormRelu` -> `MaxPooling2D` (tf2/resnet.py:593-611) on the conv output y
+        [N,H,W,C]: returns the pooled tensor; the BN output only ever exists inside the pooling kernel."""
+        e = get_engine()
+        assert self.relu
+        N, H, W, C = y.shape
+        mean, rstd, scale, shift = self._statistics(y, True, sums)
+        Ho, Wo = (H + 1) // 2, (W + 1) // 2
+        out = e.empty((N, Ho, Wo, C), y.dtype)
+        argmax = e.empty((N, Ho, Wo, C), torch.uint8)
+        lib.bn_relu_maxpool_fwd(y, e.code(y.dtype), scale, shift, out, argmax, N, H, W, C, stream_ptr())
+        self.saved = ('pool', y, argmax, mean, rstd, scale, shift)
+        return out
+
+    def backward_maxpool(self, d, d2=None):
+        """d (+ d2): gradient(s) w.r.t. the pooled tensor.  Returns d(conv output)."""
+        e = get_engine()
+        _, y, argmax, mean, rstd, scale, shift = self.saved
+        self.saved = None
+        N, H, W, C = y.shape
+        st = stream_ptr()
+        sums = e.sums(2 * C)
+        lib.maxpool_bn_bwd_reduce(d, d2, argmax, y, e.code(y.dtype), N, H, W, C, mean, rstd, scale, shift, sums, st)
+        coef = self._coefficients(sums, N * H * W, mean, rstd)
+        dy = e.empty(y.shape, y.dtype)
+        lib.maxpool_bn_bwd_apply(d, d2, argmax, y, e.code(y.dtype), dy, N, H, W, C, coef, scale, shift, st)
+        return dy
+
+    @staticmethod
+    def pool_fusable(C, dtype):
+        v = 8 if dtype == torch.bfloat16 else 4
+        return C % 8 == 0 and 256 % (C // v) == 0
+
+    def __call__(self, inputs, training, residual=None, relu=None, out_dtype=None, sums=None):
+        """`sums`: [2C] fp64 sum / sum of squares already produced by the conv epilogue."""
+        e = get_engine()
+        relu = self.relu if relu is None else relu
+        C = self.C
+        y = inputs
+        rows = y.numel() // C
+        st = stream_ptr()
+        mean, rstd, scale, shift = self._statistics(y, training, sums)
         z = e.empty(y.shape, out_dtype or y.dtype)
         tail = relu and residual is not None
         bits = None
@@ -104,23 +168,9 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
                 lib.bn_apply(y, e.code(y.dtype), None, zmask, e.code(zmask.dtype), rows, C, remask[0], remask[1], 1, st)
             lib.bn_bwd_reduce(dz, dz2, zmask, e.code(dz.dtype), y, e.code(y.dtype), rows, C, mean, rstd, sums, st)
             msc = msh = None
-        sums_g, count = sums, float(rows)
         dy = e.empty(y.shape, dy_dtype or e.act_dtype)
-        coef = e.empty((3 * C,), torch.float32)
-        gam = None if self.gamma is None else self.gamma.value
-        dgam = None if self.gamma is None else self.gamma.grad
-        dbet = None if self.beta is None else self.beta.grad
-        if e.sync_bn and e.ctx.comm is not None and 2 * C * 8 <= e.ctx.comm.slot_bytes:
-            e.ctx.comm.bn_bwd_coef(sums, count, mean, rstd, gam, coef, dgam, dbet, C)
-            lib.bn_bwd_apply_coef(dz, e.code(dz.dtype), y, e.code(y.dtype), dy, e.code(dy.dtype), rows, C, coef,
-                                  msc, msh, st)
-            return dy
-        if e.sync_bn:
-            sums_g = sums.clone()
-            e.ctx.all_reduce_sum(sums_g)
-            count *= e.ctx.num_replicas_in_sync
-        lib.bn_bwd_apply(dz, e.code(dz.dtype), y, e.code(y.dtype), dy, e.code(dy.dtype), rows, C, mean, rstd,
-                         gam, sums_g, sums, count, dgam, dbet, coef, msc, msh, st)
+        coef = self._coefficients(sums, rows, mean, rstd)
+        lib.bn_bwd_apply_coef(dz, e.code(dz.dtype), y, e.code(y.dtype), dy, e.code(dy.dtype), rows, C, coef, msc, msh, st)
         return dy
 
 
@@ -659,16 +709,26 @@ class Resnet:  # pylint: disable=missing-docstring
         st = stream_ptr()
         train_all = training
         training = train_all and not self.stem_frozen          # frozen layers: inference-mode BN, nothing saved
-        if endpoints is not None:
-            x = self.stem_conv(inputs, training)
-            endpoints['initial_conv'] = x
-            x = self.stem_bn(x, training)
-        else:
-            x = conv_bn(self.stem_conv, self.stem_bn, inputs, training)
-        for conv, bn in self.stem_extra:
-            x = conv_bn(conv, bn, x, training)
+        layers = [(self.stem_conv, self.stem_bn)] + list(self.stem_extra)
+        last_bn = layers[-1][1]
+        # training: the last stem BatchNorm + ReLU is applied inside the max-pooling kernel (its output is never stored)
+        fuse_pool = (training and not self.cifar_stem and endpoints is None and
+                     BatchNormRelu.pool_fusable(last_bn.C, e.act_dtype))
+        x = inputs
+        for i, (conv, bn) in enumerate(layers):
+            op = conv.op
+            if fuse_pool and i == len(layers) - 1:
+                sums = e.sums(2 * op.cout)
+                x = bn.forward_maxpool(op.forward(x, training, bn_sums=sums), sums)
+            elif endpoints is not None and i == 0:
+                x = conv(x, training)
+                endpoints['initial_conv'] = x
+                x = bn(x, training)
+            else:
+                x = conv_bn(conv, bn, x, training)
+        self._pool_fused = fuse_pool
         pool_saved = None
-        if not self.cifar_stem:                                   # MaxPooling2D(3, 2, 'SAME'), :605-611
+        if not self.cifar_stem and not fuse_pool:                 # MaxPooling2D(3, 2, 'SAME'), :605-611
             N, H, W, C = x.shape
             Ho, Wo = (H + 1) // 2, (W + 1) // 2
             y = e.empty((N, Ho, Wo, C))
@@ -706,17 +766,21 @@ class Resnet:  # pylint: disable=missing-docstring
             d, d2 = self.block_groups[i].backward(d, d2)
         if self.stem_frozen:
             return
-        if pool_saved is not None:
+        layers = [(self.stem_conv, self.stem_bn)] + list(self.stem_extra)
+        if self._pool_fused:
+            conv, bn = layers.pop()
+            dy = bn.backward_maxpool(d, d2)          # pooling backward + BatchNorm backward, no dz tensor
+            d, d2 = conv.backward(dy, need_dx=bool(layers)), None
+        elif pool_saved is not None:
             argmax, (N, H, W, C) = pool_saved
             lib.add_inplace(d, d2, e.code(d.dtype), d.numel(), st)
             dx = e.empty((N, H, W, C))
             lib.maxpool3x3s2_bwd(d, argmax, dx, e.code(d.dtype), N, H, W, C, st)
             d, d2 = dx, None
-        for conv, bn in reversed(self.stem_extra):
-            d = conv.backward(bn.backward(d, d2))
+        while layers:
+            conv, bn = layers.pop()
+            d = conv.backward(bn.backward(d, d2), need_dx=bool(layers))
             d2 = None
-        dy = self.stem_bn.backward(d, d2)
-        self.stem_conv.backward(dy, need_dx=False)
 
 
 MODEL_PARAMS = {  # tf2/resnet.py:709-734

@@ -79,6 +79,11 @@ def test_finetune_step_parity(flags, optimizer, ft_block, selector):
     f6, lab = structured_batch(16, 64, num_classes=100, seed=2)
     f = f6[..., :3].contiguous()
     info = OS.forward_backward(om, P, S_, [f], [lab])
+    # conditioning of this hand-warmed state: the fp32 oracle's own distance from the fp64 oracle, per tensor
+    P64 = collections.OrderedDict((k, v.double()) for k, v in P.items())
+    S64 = collections.OrderedDict((k, v.double()) for k, v in S_.items())
+    i64 = OS.forward_backward(om, P64, S64, [f.double()], [lab.double()])
+    intrinsic = {k: rel_err(info['grads'][k], i64['grads'][k]) for k in P if i64['grads'][k].norm() > 0}
     lr = 0.05
     trainer.optimizer.learning_rate = lr
     before = {v.name: v.value.clone() for v in trainer.model.variables}
@@ -90,7 +95,8 @@ def test_finetune_step_parity(flags, optimizer, ft_block, selector):
         if ref.norm() == 0:
             assert float(v.grad.abs().max()) < 1e-7 * (1 + float(ref.abs().max())), v.name
         else:
-            assert rel_err(v.grad, ref) < 2e-3, (v.name, rel_err(v.grad, ref))      # hand-warmed BN state: see test_gpu_step.py on conditioning
+            err = rel_err(v.grad, i64['grads'][v.name])
+            assert err < max(2e-3, 5 * intrinsic[v.name]), (v.name, err, intrinsic[v.name])   # see test_gpu_step.py on conditioning
     Pt = collections.OrderedDict((k, P[k]) for k in names_t)
     Gt = collections.OrderedDict((k, info['grads'][k]) for k in names_t)
     Z = collections.OrderedDict((k, torch.zeros_like(v)) for k, v in Pt.items())
