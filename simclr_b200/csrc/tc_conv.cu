@@ -1223,6 +1223,8 @@ static int wgrad_tc_impl(const void* x, const void* dy, float* dw, int dtype, in
     set_error("conv2d_wgrad_tc: fp32 operands are not supported (use conv2d_wgrad_simt)");
     return SIMCLR_ERR_UNSUPPORTED;
   }
+  if (halo3x3_wgrad_applicable(dtype, N, H, W, Cs, Cin, Cout, R, S, stride, x, dy, dw))
+    return run_halo3x3_wgrad(x, dy, dw, N, H, W, st, zero);
   const int es = dtype == SIMCLR_BF16 ? 2 : 4;
   const int ATOM_E = 128 / es, CH = 16 / es;
   bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);

@@ -291,6 +291,140 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, CFG::TMEM_COLS); }
 }
 
+// ===========================================================================
+// wgrad of the 64 -> 64 channel 3x3 layers with halo reuse.
+//   dW[(r,s,c)][co] = sum over pixels  X[pixel + (r,s)][c] * dY[pixel][co]
+// Both operands are MN-major (the reduction K runs over pixels, rows of 128 bytes): the X slab of a tile is the
+// fprop slab, tap (r, s) is the slab shifted by r*Wp + s rows along K, and TWO taps share one M = 128 operand --
+// the second 64-channel atom sits LBO = (offset difference) * 128 bytes after the first, i.e. the atoms overlap in
+// shared memory (scripts/probe_umma_mn_shift.cu: tcgen05 takes any 128-byte multiple for the start and for LBO).
+// Five accumulators [128 x 64] (tap pairs (0,1) (2,3) (4,5) (6,7) (8,8)) live in TMEM for the whole kernel: every
+// CTA sweeps its tiles, then adds its [576 x 64] partial into dW with TMA reduce-add.  The generic wgrad kernel
+// re-fetches X once per tap and dY once per 128 filter rows: 120 KB of L2 -> SM traffic per 64 pixels against
+// 24 KB here.  dY columns outside the image arrive as zeros (TMA out-of-bounds fill), buffer rows the boxes never
+// write are zeroed once, so virtual pixels contribute nothing.
+// ===========================================================================
+constexpr int WG_DY_BYTES = 128 * 128;                       // [128 virtual pixels][64 co]
+constexpr int WG_STAGE_BYTES = SLAB_BYTES + WG_DY_BYTES;     // 48 KB
+constexpr int WG_STAGES = 3;
+constexpr size_t WG_SMEM = 1024 + (size_t)WG_STAGES * WG_STAGE_BYTES + 2 * EPI_TILE + 256;
+
+__global__ void __launch_bounds__(192, 1)
+halo3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                     const __grid_constant__ CUtensorMap tmap_dw, const HaloGeom g) {
+  constexpr uint32_t IDESC = make_idesc(false, 128, 64, true, true);
+  constexpr uint32_t HI = desc_hi_sw128(1024);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* epi = smem + (size_t)WG_STAGES * WG_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + 2 * EPI_TILE);
+  uint64_t* full = bars;                     // [WG_STAGES]
+  uint64_t* empty = bars + WG_STAGES;        // [WG_STAGES]
+  uint64_t* acc_full = empty + WG_STAGES;    // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // zero the operand ring once: the TMA boxes never write the tail rows, and 0 * stale NaN would poison the sums
+  for (int i = threadIdx.x; i < WG_STAGES * WG_STAGE_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_dy); tma_prefetch_desc(&tmap_dw); }
+  if (warp == 4) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const bool has_work = (int)blockIdx.x < g.num_tiles;
+
+  if (warp < 4) {
+    // ------------------------------ epilogue (once) ------------------------------
+    if (has_work) {
+      mbar_wait(acc_full, 0, 210);
+      tc_fence_after();
+      const int row = warp * 32 + lane;
+      uint32_t box_ctr = 0;
+#pragma unroll 1
+      for (int pr = 0; pr < 5; ++pr) {
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc, ++box_ctr) {
+          uint8_t* stage = epi + (box_ctr & 1) * EPI_TILE;
+          if (threadIdx.x == 0) tma_store_wait_read<1>();
+          named_barrier_sync(1, 128);
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + pr * 64 + cc * 32, acc);
+          tmem_ld_wait();
+          const uint32_t srow = smem_u32(stage);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            sts16h(srow + sw128_offset(row, q), make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+          fence_proxy_async();
+          named_barrier_sync(1, 128);
+          // rows of accumulator `pr` are filter rows [pr*128, pr*128 + 128) of the [9*64][64] matrix; the duplicate
+          // tap of the last pair lands at rows >= 576 and is clipped by the tensor map
+          if (threadIdx.x == 0) { tma_reduce_add_2d(&tmap_dw, stage, cc * 32, pr * 128); tma_store_commit(); }
+        }
+      }
+      if (threadIdx.x == 0) tma_store_wait_all<0>();
+    }
+  } else if (warp == 4) {
+    // ------------------------------ MMA issuer ----------------------------
+    int ss = 0; uint32_t sphase = 0;
+    const uint32_t smem_lo = uniform_u32((smem_u32(smem) & 0x3FFFFu) >> 4);
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    const int Wp = g.Wp;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&full[ss], sphase, 220);
+      tc_fence_after();
+      const uint32_t x_lo = smem_lo + (uint32_t)ss * (WG_STAGE_BYTES >> 4);
+      const uint32_t dy_lo = x_lo + (SLAB_BYTES >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int pr = 0; pr < 5; ++pr) {
+          const int ta = 2 * pr, tb = pr == 4 ? 8 : 2 * pr + 1;
+          const int offa = (ta / 3) * Wp + ta % 3, offb = (tb / 3) * Wp + tb % 3;
+          const uint32_t a_lo = (x_lo + (uint32_t)offa * 8u) | ((((uint32_t)(offb - offa) * 8u) & 0x3FFFu) << 16);   // LBO = (offb - offa) * 128 B
+          const uint32_t b_lo = dy_lo | (1u << 16);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)        // 16 pixels (16 rows of 128 B) per MMA
+            umma<false>(tmem_u + pr * 64, desc_pack(a_lo + k * 128, HI), desc_pack(b_lo + k * 128, HI), IDESC,
+                        (!first || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[ss]);
+      }
+      __syncwarp();
+      first = false;
+      if (++ss == WG_STAGES) { ss = 0; sphase ^= 1; }
+    }
+    if (has_work && elect_one()) umma_commit(acc_full);
+    __syncwarp();
+  } else {
+    // ------------------------------ TMA producer --------------------------
+    if (lane == 0) {
+      int ss = 0; uint32_t sphase = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const int n = tile / g.tiles_per_img, p0 = (tile - n * g.tiles_per_img) * g.TR;
+        mbar_wait(&empty[ss], sphase ^ 1, 230);
+        uint8_t* st = smem + (size_t)ss * WG_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[ss], g.box_bytes + g.TR * g.Wp * 128);
+        tma_load_4d(st, &tmap_x, &full[ss], 0, -1, p0 - 1, n);
+        tma_load_4d(st + SLAB_BYTES, &tmap_dy, &full[ss], 0, 0, p0, n);
+        if (++ss == WG_STAGES) { ss = 0; sphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // rank-4 tiled map over an NHWC tensor {C, W, H, N}, boxes {64 channels, bw, bh, 1}, 128B swizzle, zero fill
 int make_tmap_nhwc_tiled(CUtensorMap* map, const void* base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t bw,
                          uint32_t bh) {
@@ -374,6 +508,44 @@ int run_halo3x3(int mode, const void* src, const void* wk, void* out, int64_t N,
                               : launch_halo<64, 1, true, false>(tx, tw, ty, g, nullptr, st);
   return bn_sums ? launch_halo<128, 2, false, true>(tx, tw, ty, g, bn_sums, st)
                  : launch_halo<128, 2, false, false>(tx, tw, ty, g, nullptr, st);
+}
+
+bool halo3x3_wgrad_applicable(int dtype, int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cin, int64_t Cout, int64_t R,
+                              int64_t S, int64_t stride, const void* x, const void* dy, const void* dw) {
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("SIMCLR_TC_HALO_WGRAD"); en = (e && e[0] == '0') ? 0 : 1; }
+  if (!en || !halo_enabled() || dtype != SIMCLR_BF16 || R != 3 || S != 3 || stride != 1) return false;
+  if (Cs != 64 || Cin != 64 || Cout != 64) return false;
+  const int64_t Wp = W + 2;
+  if (Wp > 64) return false;
+  const int64_t TR = 128 / Wp;
+  if (TR < 1) return false;
+  const int64_t tiles_per_img = (H + TR - 1) / TR;
+  if ((double)(H * W) / (double)(tiles_per_img * 128) < 0.80) return false;
+  if (N * tiles_per_img >= (1ll << 31)) return false;
+  if (!aligned16(x) || !aligned16(dy) || !aligned16(dw)) return false;
+  return get_encode_tiled() != nullptr;
+}
+
+int run_halo3x3_wgrad(const void* x, const void* dy, float* dw, int64_t N, int64_t H, int64_t W, cudaStream_t st, bool zero) {
+  HaloGeom g;
+  g.H = (int)H; g.W = (int)W; g.Wp = (int)W + 2; g.TR = 128 / g.Wp; g.N = (int)N;
+  g.tiles_per_img = (int)((H + g.TR - 1) / g.TR); g.num_tiles = (int)(N * g.tiles_per_img);
+  g.box_bytes = (g.TR + 2) * g.Wp * 128; g.n_out = 64; g.C = 64; g.tap_base = 0; g.tap_sign = 1;
+  CUtensorMap tx, tdy, tdw;
+  int rc = make_tmap_nhwc_tiled(&tx, x, (uint64_t)N, (uint64_t)H, (uint64_t)W, 64, (uint32_t)g.Wp, (uint32_t)(g.TR + 2));
+  if (rc) return rc;
+  rc = make_tmap_nhwc_tiled(&tdy, dy, (uint64_t)N, (uint64_t)H, (uint64_t)W, 64, (uint32_t)g.Wp, (uint32_t)g.TR);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tdw, dw, 4, 9 * 64, 64, 64 * 4, 128, 32);
+  if (rc) return rc;
+  if (zero && !accumulate_prezeroed()) SIMCLR_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * 64 * 64 * sizeof(float), st));
+  cudaError_t e = cudaFuncSetAttribute(halo3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM);
+  if (e != cudaSuccess) { set_error("halo3x3_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
+  halo3x3_wgrad_kernel<<<grid, 192, WG_SMEM, st>>>(tx, tdy, tdw, g);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
 }
 
 }  // namespace tc

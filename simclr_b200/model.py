@@ -274,6 +274,11 @@ class Model:
 
     def backward(self, d_projection_head_outputs, d_supervised_head_outputs=None):
         """Explicit `tape.gradient` (tf2/run.py:621): fills `.grad` of every trainable variable."""
+        self.backward_bottom(self.backward_top(d_projection_head_outputs, d_supervised_head_outputs, 0), 0)
+
+    def backward_top(self, d_projection_head_outputs, d_supervised_head_outputs=None, split=0):
+        """Heads + block groups [split, 4): after it the gradients of every variable from the first one of block
+        group `split`+1 to the end of the flat buffer are final (see `grad_split_offset`)."""
         d_sup_in = None
         if d_supervised_head_outputs is not None:
             d_sup_in = self.supervised_head.backward(d_supervised_head_outputs)
@@ -288,4 +293,16 @@ class Model:
             d_hiddens = self._projection_head.backward(d_sup_in, upto=sel)
         else:
             d_hiddens = self._projection_head.backward(d_projection_head_outputs)
-        self.resnet_model.backward(d_hiddens)
+        return self.resnet_model.backward_top(d_hiddens, split)
+
+    def backward_bottom(self, state, split=0):
+        self.resnet_model.backward_bottom(state, split)
+
+    def grad_split_offset(self, split):
+        """Element offset in the flat gradient buffer of the first variable of block group `split`+1: everything
+        from there on (later groups, projection head, supervised head) is produced by `backward_top`."""
+        tag = '/block_group%d/' % (split + 1)
+        for v in self.vs.trainable:
+            if tag in v.name:
+                return (v.grad.data_ptr() - self.vs.flat_grad.data_ptr()) // 4
+        return None

@@ -753,6 +753,13 @@ class Resnet:  # pylint: disable=missing-docstring
         return out
 
     def backward(self, d_hiddens):
+        self.backward_bottom(self.backward_top(d_hiddens, 0), 0)
+
+    def backward_top(self, d_hiddens, split):
+        """Backward through the mean over H,W and block groups [split, 4) -- the last groups hold almost all of the
+        parameters (ResNet-50: groups 3-4 + heads = 96 %) but little of the backward time, so a data-parallel step
+        can start reducing their gradients while `backward_bottom` is still running.  Returns the state
+        `backward_bottom(state, split)` continues from (None: a frozen boundary was reached)."""
         e = get_engine()
         st = stream_ptr()
         pool_saved, (N, H, W, C) = self.saved
@@ -760,9 +767,21 @@ class Resnet:  # pylint: disable=missing-docstring
         d = e.empty((N, H, W, C))
         lib.global_avgpool_bwd(d_hiddens, e.code(d_hiddens.dtype), d, e.code(d.dtype), N, H * W, C, st)
         d2 = None
-        for i in reversed(range(len(self.block_groups))):
+        for i in reversed(range(split, len(self.block_groups))):
             if self.stem_frozen and i < self.frozen_groups:
-                return                      # tf.stop_gradient in front of block group `fine_tune_after_block` + 1
+                return None                 # tf.stop_gradient in front of block group `fine_tune_after_block` + 1
+            d, d2 = self.block_groups[i].backward(d, d2)
+        return (d, d2, pool_saved)
+
+    def backward_bottom(self, state, split):
+        if state is None:
+            return
+        e = get_engine()
+        st = stream_ptr()
+        d, d2, pool_saved = state
+        for i in reversed(range(0, split)):
+            if self.stem_frozen and i < self.frozen_groups:
+                return
             d, d2 = self.block_groups[i].backward(d, d2)
         if self.stem_frozen:
             return

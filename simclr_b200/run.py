@@ -37,34 +37,80 @@ class Trainer:
         self.optimizer = model_lib.build_optimizer(self.learning_rate)
         self.metrics = {}
         self._graph = None
+        self._graph_bottom = None
+        self._graph_apply = None
         self._static = None
+        self._bw_state = None
+        self._split_off = None
+        self._side = None
+        self._top_work = None
 
     # ------------------------------------------------------------------
+    GRAD_SPLIT = 2      # backward_top covers block groups 3-4 + heads: 96 % of the ResNet-50 gradient bytes
+
     def single_step(self, features, labels):
         """One synchronous data-parallel step on this replica's shard.
 
         features [B,H,W,6] fp32, labels one-hot [B,classes] fp32 (or None).
         Loss = contrastive + supervised + weight decay, divided by the number of
         replicas (tf2/run.py:587-617); gradients are summed across replicas
-        (Keras `apply_gradients`, C3) and LARS is applied."""
-        loss = self.forward_backward(features, labels)
-        self.reduce_gradients()
+        (Keras `apply_gradients`, C3) and LARS is applied.  With more than one replica the gradient
+        all-reduce of the late layers runs on a side stream under the backward pass of the early ones."""
+        if self._overlap_ok():
+            loss = self.forward_backward_top(features, labels)
+            self.reduce_gradients_top_async()
+            self.backward_bottom()
+            self.reduce_gradients_bottom()
+        else:
+            loss = self.forward_backward(features, labels)
+            self.reduce_gradients()
         self.optimizer.apply_gradients([(v.grad, v) for v in self.model.trainable_variables])
         return loss
+
+    def _overlap_ok(self):
+        if self.strategy.num_replicas_in_sync < 2 or FLAGS.train_mode != 'pretrain' or 'lars' not in FLAGS.optimizer:
+            return False
+        if os.environ.get('SIMCLR_GRAD_OVERLAP', '1') == '0':
+            return False
+        if self._split_off is None:
+            off = self.model.grad_split_offset(self.GRAD_SPLIT)
+            self._split_off = off if off else -1
+        return self._split_off > 0
 
     def forward_backward(self, features, labels):
         """Forward, losses and the explicit backward pass: fills `.grad` of every trainable
         variable with THIS replica's contribution.  The collectives inside (SyncBN statistics,
         embedding / log-sum-exp all-gathers) are our own peer-memory kernels when
         `strategy.comm` is set, so this part is CUDA-graph capturable at any replica count."""
-        e, model, R = self.engine, self.model, self.strategy.num_replicas_in_sync
+        loss = self.forward_backward_top(features, labels, split=0)
+        self.backward_bottom(split=0)
+        return loss
+
+    def forward_backward_top(self, features, labels, split=None):
+        """Forward, losses, and the backward pass down to block group `split`+1 (all of it for split 0)."""
+        e, model = self.engine, self.model
+        split = self.GRAD_SPLIT if split is None else split
         e.begin_step(model.vs.flat_grad)       # BN-sum pool and the flat gradient buffer zeroed once
         try:
-            return self._forward_backward(features, labels)
-        finally:
+            return self._forward_backward_top(features, labels, split)
+        except BaseException:
             e.end_step()
+            raise
 
-    def _forward_backward(self, features, labels):
+    def backward_bottom(self, split=None):
+        split = self.GRAD_SPLIT if split is None else split
+        try:
+            self.model.backward_bottom(self._bw_state, split)
+            if 'lars' not in FLAGS.optimizer:       # every gradient is final now
+                R = self.strategy.num_replicas_in_sync
+                for v in self.model.trainable_variables:
+                    if 'batch_normalization' not in v.name and v.grad is not None:
+                        lib.axpy(float(FLAGS.weight_decay) / R, v.value, v.grad, v.numel, stream_ptr())
+        finally:
+            self._bw_state = None
+            self.engine.end_step()
+
+    def _forward_backward_top(self, features, labels, split):
         e, model, R = self.engine, self.model, self.strategy.num_replicas_in_sync
         st = stream_ptr()
         projection_head_outputs, supervised_head_outputs = model(features, training=True)
@@ -90,22 +136,39 @@ class Trainer:
         self.metrics['weight_decay'] = weight_decay
         loss = loss + weight_decay
         self.metrics['total_loss'] = loss
-        model.backward(d_proj, d_sup)
+        self._bw_state = model.backward_top(d_proj, d_sup, split)
         # d(weight_decay)/dW = wd * W (loss / R per replica): with LARS on the supervised-head kernel only (the
-        # optimizer decays the rest), otherwise on every non-BatchNorm variable (tf2/model.py:47-69)
-        for v in model.trainable_variables:
-            if 'lars' in FLAGS.optimizer:
-                decayed = 'head_supervised' in v.name and 'bias' not in v.name
-            else:
-                decayed = 'batch_normalization' not in v.name
-            if decayed and v.grad is not None:
-                lib.axpy(float(FLAGS.weight_decay) / R, v.value, v.grad, v.numel, st)
+        # optimizer decays the rest; its gradient is final here), otherwise on every non-BatchNorm variable
+        # (tf2/model.py:47-69) -- those runs do not split the backward pass
+        assert split == 0 or 'lars' in FLAGS.optimizer
+        if 'lars' in FLAGS.optimizer:
+            for v in model.trainable_variables:
+                if 'head_supervised' in v.name and 'bias' not in v.name and v.grad is not None:
+                    lib.axpy(float(FLAGS.weight_decay) / R, v.value, v.grad, v.numel, st)
         return loss
 
     def reduce_gradients(self):
         """C3: cross-replica SUM of the gradients, one NCCL all-reduce over the flat buffer."""
         if self.strategy.num_replicas_in_sync > 1:
             self.strategy.all_reduce_sum(self.model.vs.flat_grad)
+
+    def reduce_gradients_top_async(self):
+        """All-reduce of the gradients `forward_backward_top` has finished (block groups 3-4 + heads: the tail of
+        the flat buffer) on a side stream: it runs under `backward_bottom`."""
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            self._top_work = dist.all_reduce(self.model.vs.flat_grad[self._split_off:], op=dist.ReduceOp.SUM,
+                                             group=self.strategy.group, async_op=True)
+
+    def reduce_gradients_bottom(self):
+        dist.all_reduce(self.model.vs.flat_grad[:self._split_off], op=dist.ReduceOp.SUM, group=self.strategy.group)
+        self._top_work.wait()                   # the current stream waits for the side-stream all-reduce
+        torch.cuda.current_stream().wait_stream(self._side)
+        self._top_work = None
 
     # ------------------------------------------------------------------
     def capture(self, features, labels, warmup=2, restore=False):
@@ -146,11 +209,19 @@ class Trainer:
                 raise RuntimeError('CUDA-graph capture with %d replicas needs the peer-memory collectives '
                                    '(strategy.comm); run eagerly instead' % R)
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._graph_loss = self.forward_backward(features, labels)
+            self._graph_bottom = None
+            if self._overlap_ok():
+                # three graphs: [forward + backward of groups 3-4 and heads] | all-reduce of their gradients on a side
+                # stream, under [backward of groups 1-2 and the stem] | all-reduce of the rest | [LARS]
+                with torch.cuda.graph(self._graph):
+                    self._graph_loss = self.forward_backward_top(features, labels)
+                self._graph_bottom = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph_bottom, pool=self._graph.pool()):
+                    self.backward_bottom()
+            else:
+                with torch.cuda.graph(self._graph):
+                    self._graph_loss = self.forward_backward(features, labels)
             self._graph_apply = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph_apply):
-                self.optimizer.apply_gradients([(v.grad, v) for v in self.model.trainable_variables])
         if snap is not None:
             vs.flat_value.copy_(snap[0]); vs.flat_moving.copy_(snap[1]); opt._flat_v.copy_(snap[2])
             opt.iterations = snap[3]
@@ -160,7 +231,12 @@ class Trainer:
         self.optimizer.prepare_replay()
         self._graph.replay()
         if self._graph_apply is not None:
-            self.reduce_gradients()
+            if self._graph_bottom is not None:
+                self.reduce_gradients_top_async()
+                self._graph_bottom.replay()
+                self.reduce_gradients_bottom()
+            else:
+                self.reduce_gradients()
             self._graph_apply.replay()
         return self._graph_loss
 

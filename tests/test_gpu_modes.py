@@ -107,8 +107,15 @@ def test_finetune_step_parity(flags, optimizer, ft_block, selector):
     else:
         Pn, _ = OL.lars_apply(Pt, Gt, Z, lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay,
                               exclude_from_weight_decay=OL.LARS_EXCLUDE)
+    # the applied UPDATE against the oracle's: SGD / LARS updates are linear in the gradient (1e-2 covers the 2e-3
+    # gradient bar); Adam's first step is lr * g / (|g| + eps') -- a sign function of every element, so the elements
+    # whose gradient is within the 1e-3 error band of zero move by +-lr in either direction
+    utol = 0.1 if optimizer == 'adam' else 1e-2
     for v in trainer.model.trainable_variables:
-        assert rel_err(v.value, Pn[v.name]) < 2e-3, v.name       # adam: m / sqrt(v) amplifies 1e-3 gradient differences
+        upd, upd_ref = v.value - before[v.name], Pn[v.name] - Pt[v.name]
+        if upd_ref.norm() > 0:
+            assert rel_err(upd, upd_ref) < utol, (v.name, rel_err(upd, upd_ref))
+        assert rel_err(v.value, Pn[v.name]) < (2e-2 if optimizer == 'adam' else 2e-3), v.name
     for v in trainer.model.variables:
         if v.name in frozen or (ft_block >= 0 and v.name in S_ and v.name in frozen):
             assert torch.equal(v.value, before[v.name]), 'frozen variable %s changed' % v.name

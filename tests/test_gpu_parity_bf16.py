@@ -130,9 +130,9 @@ def test_bf16_tc_loss_curve_20_steps(flags):
     print('relative deviation from fp32: cuda max %.2e mean %.2e | bf16-storage oracle max %.2e mean %.2e'
           % (max(dev), sum(dev) / steps, max(dev_e), sum(dev_e) / steps))
     assert min(ref[-5:]) < ref[0] - 0.5, 'the trajectory must actually train (loss falls)'
-    assert max(dev[:4]) < 8e-3, dev             # before the trajectories decorrelate
-    assert max(dev) < 6e-2 and sum(dev) / steps < 3e-2, dev
-    assert sum(dev) / steps < 2.0 * sum(dev_e) / steps + 5e-3, (dev, dev_e)
+    assert max(dev[:3]) < 5e-3, dev             # before the trajectories decorrelate
+    assert max(dev) < 1.5 * max(dev_e) + 2e-2, (max(dev), max(dev_e))
+    assert sum(dev) / steps < 1.5 * sum(dev_e) / steps + 5e-3, (dev, dev_e)
     assert abs(sum(ours[-5:]) - sum(ref[-5:])) / sum(ref[-5:]) < 2e-2     # same loss level after 20 steps
 
 
