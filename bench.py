@@ -325,12 +325,15 @@ def run_b200(args):
                 and args.sk_ratio == 0 and args.engine == 'tc':
             try:
                 tr = json.load(open(tj))
-                traffic = tr['dram_bytes_per_launch']; traffic_src = 'profiles/traffic.json (%s)' % tr['source']
+                # per conv CALL of this run (a strided dgrad call is up to 4 parity-class kernels: ncu counts
+                # tr['launches'] kernels for the n_launch calls timed here)
+                traffic = tr['dram_bytes_per_step'] / n_launch
+                traffic_src = 'profiles/traffic.json (%s; %d kernel launches for %d conv calls)' % (tr['source'], tr['launches'], n_launch)
             except Exception:
                 traffic = None
         key = (args.resnet_depth, args.width_multiplier, S, args.sk_ratio > 0)
         step_tflops = (ips / world) * GFLOP_PER_IMAGE[key] / 1e3 if key in GFLOP_PER_IMAGE else None
-        roof = {'bound': 'tensor', 'kernel': 'igemm_kernel/wgrad_kernel (tcgen05 implicit GEMM, %d launches/step)' % sum(v[2] for v in by.values()),
+        roof = {'bound': 'tensor', 'kernel': 'igemm / wgrad / halo3x3 kernels (tcgen05 implicit GEMM, %d conv calls per step)' % sum(v[2] for v in by.values()),
                 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops'],
                 'traffic': traffic, 'traffic_source': traffic_src, 'algorithmic_bytes': alg / n_launch,
                 'peak_source': peaks['which'],

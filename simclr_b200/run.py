@@ -222,6 +222,8 @@ class Trainer:
                 with torch.cuda.graph(self._graph):
                     self._graph_loss = self.forward_backward(features, labels)
             self._graph_apply = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_apply, pool=self._graph.pool()):
+                self.optimizer.apply_gradients([(v.grad, v) for v in self.model.trainable_variables])
         if snap is not None:
             vs.flat_value.copy_(snap[0]); vs.flat_moving.copy_(snap[1]); opt._flat_v.copy_(snap[2])
             opt.iterations = snap[3]

@@ -97,8 +97,11 @@ def test_finetune_step_parity(flags, optimizer, ft_block, selector):
         else:
             err = rel_err(v.grad, i64['grads'][v.name])
             assert err < max(2e-3, 5 * intrinsic[v.name]), (v.name, err, intrinsic[v.name])   # see test_gpu_step.py on conditioning
-    Pt = collections.OrderedDict((k, P[k]) for k in names_t)
-    Gt = collections.OrderedDict((k, info['grads'][k]) for k in names_t)
+    # the optimizer step, isolated from the gradient tolerance: the oracle's update rule applied to the gradients the
+    # CUDA step produced must give the CUDA step's weights (Adam's first step is ~lr * sign(g): comparing against
+    # the update from the ORACLE's gradients would flip every element whose gradient lies within the 1e-3 band of 0)
+    Pt = collections.OrderedDict((k, P[k].double()) for k in names_t)
+    Gt = collections.OrderedDict((v.name, v.grad.detach().double().cpu()) for v in trainer.model.trainable_variables)
     Z = collections.OrderedDict((k, torch.zeros_like(v)) for k, v in Pt.items())
     if optimizer == 'momentum':
         Pn, _ = OO.sgd_nesterov_apply(Pt, Gt, Z, lr, cfg.momentum, True)
@@ -107,15 +110,10 @@ def test_finetune_step_parity(flags, optimizer, ft_block, selector):
     else:
         Pn, _ = OL.lars_apply(Pt, Gt, Z, lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay,
                               exclude_from_weight_decay=OL.LARS_EXCLUDE)
-    # the applied UPDATE against the oracle's: SGD / LARS updates are linear in the gradient (1e-2 covers the 2e-3
-    # gradient bar); Adam's first step is lr * g / (|g| + eps') -- a sign function of every element, so the elements
-    # whose gradient is within the 1e-3 error band of zero move by +-lr in either direction
-    utol = 0.1 if optimizer == 'adam' else 1e-2
     for v in trainer.model.trainable_variables:
-        upd, upd_ref = v.value - before[v.name], Pn[v.name] - Pt[v.name]
+        upd, upd_ref = (v.value.double().cpu() - Pt[v.name]), Pn[v.name] - Pt[v.name]
         if upd_ref.norm() > 0:
-            assert rel_err(upd, upd_ref) < utol, (v.name, rel_err(upd, upd_ref))
-        assert rel_err(v.value, Pn[v.name]) < (2e-2 if optimizer == 'adam' else 2e-3), v.name
+            assert rel_err(upd, upd_ref) < 1e-4, (v.name, rel_err(upd, upd_ref))
     for v in trainer.model.variables:
         if v.name in frozen or (ft_block >= 0 and v.name in S_ and v.name in frozen):
             assert torch.equal(v.value, before[v.name]), 'frozen variable %s changed' % v.name
