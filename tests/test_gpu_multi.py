@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize('args', [['fp32', 'simt', 'global'], ['fp32', 'simt', 'local'], ['bf16', 'tc', 'global', 'graph'],
-                                  ['fp32', 'simt', 'global', 'nccl']])
+                                  ['fp32', 'simt', 'global', 'nccl']],
+                         ids=['fp32-syncbn-peer', 'fp32-localbn-peer', 'bf16-peer-graph', 'fp32-syncbn-nccl'])
 def test_two_rank_step_matches_oracle(args):
     """Default: SyncBN statistics and the embedding / lse all-gathers through the NVLink peer-memory kernels
     (csrc/comm.cu); 'nccl': the same collectives through torch.distributed.  'graph': additionally two segmented
