@@ -204,9 +204,29 @@ def run_b200(args):
     peer = trainer.strategy.comm is not None
     use_graph = (not args.no_graph) and (world == 1 or peer)
     launches0 = lib.launch_count
+    graph_note = None
     if use_graph:
-        trainer.capture(features, labels, warmup=1)
-        launches_per_step = None
+        ok = 1
+        try:
+            trainer.capture(features, labels, warmup=1)
+            trainer.replay()
+            torch.cuda.synchronize()
+        except Exception as ex:           # every rank must agree before anyone changes path
+            ok = 0
+            graph_note = 'graph / peer-memory path failed on rank %d: %r' % (rank, ex)
+            log(graph_note)
+        if world > 1:
+            t_ok = torch.tensor([ok], device=eng.device)
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            ok = int(t_ok.item())
+        if not ok:
+            # fall back for the whole job: eager launches, every collective through NCCL
+            use_graph = False
+            peer = False
+            trainer.strategy.comm = None
+            trainer._graph = trainer._graph_bottom = trainer._graph_apply = None
+            eng.end_step()
+            graph_note = graph_note or 'graph / peer-memory path failed on another rank'
     step_fn = trainer.replay if use_graph else (lambda: trainer.single_step(features, labels))
     if use_graph:
         # launches recorded during the capture pass == launches per replay
@@ -399,7 +419,7 @@ def run_b200(args):
             'data': 'synthetic',
             'config': {'workload': workload_string(args, world),
                        'l2': 'inputs larger than L2 (activations are GBs per step)',
-                       'cuda_graph': use_graph, 'parallelism': 'dp%d' % world,
+                       'cuda_graph': use_graph, 'graph_fallback': graph_note, 'parallelism': 'dp%d' % world,
                        'collectives': ('none' if world == 1 else ('nvlink peer-memory kernels (SyncBN, all-gathers) + NCCL gradient all-reduce' if peer else 'NCCL'))},
             'e2e': {'value': e2e_ips, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches_per_step * args.steps,
