@@ -202,3 +202,35 @@ def preprocess_for_train(image, height, width, draws, color_jitter_strength=1.0)
         image = random_color_jitter(image, draws['color'])
     image = image.reshape(height, width, 3)
     return torch.clamp(image, 0., 1.)
+
+
+CROP_PROPORTION = 0.875  # tf2/data_util.py:22: standard ImageNet central crop
+
+
+def _compute_crop_shape(image_height, image_width, aspect_ratio, crop_proportion):
+    """tf2/data_util.py:175-213 (tf.math.rint = round half to even on fp32 values)."""
+    import numpy as np
+    w, h = np.float32(image_width), np.float32(image_height)
+    if aspect_ratio > float(w / h):
+        crop_height = int(np.rint(np.float32(crop_proportion / aspect_ratio) * w))
+        crop_width = int(np.rint(np.float32(crop_proportion) * w))
+    else:
+        crop_height = int(np.rint(np.float32(crop_proportion) * h))
+        crop_width = int(np.rint(np.float32(crop_proportion * aspect_ratio) * h))
+    return crop_height, crop_width
+
+
+def center_crop_box(image_height, image_width, height, width, crop_proportion=CROP_PROPORTION):
+    """The (y, x, h, w) box of `center_crop` (tf2/data_util.py:216-243)."""
+    crop_height, crop_width = _compute_crop_shape(image_height, image_width, width / height, crop_proportion)
+    offset_height = ((image_height - crop_height) + 1) // 2
+    offset_width = ((image_width - crop_width) + 1) // 2
+    return offset_height, offset_width, crop_height, crop_width
+
+
+def preprocess_for_eval(image, height, width, crop=True):
+    """tf2/data_util.py:478-494 on an fp image [Hs,Ws,3] in [0,1]."""
+    if crop:
+        image = crop_and_resize_bicubic(image, center_crop_box(image.shape[0], image.shape[1], height, width), height, width)
+    image = image.reshape(height, width, 3)
+    return torch.clamp(image, 0., 1.)

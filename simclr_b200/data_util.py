@@ -139,13 +139,55 @@ def draw_train_augmentation(src_h, src_w, color_jitter_strength=1.0, rng=None):
     return dict(box=box, flip=rng.random() < 0.5, color=color)
 
 
+CROP_PROPORTION = 0.875  # Standard for ImageNet (tf2/data_util.py:22)
+
+_NO_COLOR = dict(apply_jitter=False, perm=(0, 1, 2, 3), brightness=1., contrast=1., saturation=1., hue=0., apply_gray=False)
+
+
+def _compute_crop_shape(image_height, image_width, aspect_ratio, crop_proportion):
+    """tf2/data_util.py:175-213: aspect-ratio-preserving shape of the central crop (fp32 arithmetic, round half
+    to even, as `tf.math.rint`)."""
+    import numpy as np
+    w, h = np.float32(image_width), np.float32(image_height)
+    if aspect_ratio > float(w / h):
+        crop_height = int(np.rint(np.float32(crop_proportion / aspect_ratio) * w))
+        crop_width = int(np.rint(np.float32(crop_proportion) * w))
+    else:
+        crop_height = int(np.rint(np.float32(crop_proportion) * h))
+        crop_width = int(np.rint(np.float32(crop_proportion * aspect_ratio) * h))
+    return crop_height, crop_width
+
+
+def center_crop_box(image_height, image_width, height, width, crop_proportion=CROP_PROPORTION):
+    """(y, x, h, w) of `center_crop` (tf2/data_util.py:216-243)."""
+    crop_height, crop_width = _compute_crop_shape(image_height, image_width, width / height, crop_proportion)
+    return (((image_height - crop_height) + 1) // 2, ((image_width - crop_width) + 1) // 2, crop_height, crop_width)
+
+
+def preprocess_for_eval_batch(images, height, width, crop=True, out=None, channel_offset=0):
+    """`preprocess_for_eval` (tf2/data_util.py:478-494) for a batch of uint8 images: central crop of
+    CROP_PROPORTION, bicubic resize, clip -- the crop / resize / clip stages of the augmentation kernel with the
+    flip and the colour ops switched off.  Without `crop` the images must already be height x width."""
+    draws = []
+    for im in images:
+        Hs, Ws = im.shape[0], im.shape[1]
+        if crop:
+            box = center_crop_box(Hs, Ws, height, width)
+        else:
+            if (Hs, Ws) != (height, width):
+                raise ValueError('preprocess_for_eval(crop=False) needs %dx%d images, got %dx%d' % (height, width, Hs, Ws))
+            box = (0, 0, Hs, Ws)
+        draws.append(dict(box=box, flip=False, color=_NO_COLOR))
+    return preprocess_for_train_batch(images, draws, height, width, out=out, channel_offset=channel_offset)
+
+
 def preprocess_image(image, height, width, is_training=False, color_jitter_strength=0., test_crop=True, draws=None):
     """Preprocesses the given image (tf2/data_util.py:497-518; same arguments).
 
-    image: uint8 tensor [Hs,Ws,3].  Training path only (`preprocess_for_train` on device);
-    the eval path (`center_crop`) is outside the pretrain step.  `draws` injects the random draws."""
+    image: uint8 tensor [Hs,Ws,3].  Training: `preprocess_for_train` on device (`draws` injects the random
+    draws); otherwise `preprocess_for_eval` (central crop when `test_crop`)."""
     if not is_training:
-        raise NotImplementedError('preprocess_for_eval (center crop) is not on the B200 pretrain path')
+        return preprocess_for_eval_batch([image], height, width, crop=test_crop)[0]
     if draws is None:
         draws = draw_train_augmentation(image.shape[0], image.shape[1], color_jitter_strength)
     if color_jitter_strength <= 0:

@@ -328,11 +328,22 @@ def main(argv):
         raise app.UsageError('Too many command-line arguments.')
     rank = init_distributed()
     engine_lib.set_engine(engine_lib.Engine())
-    trainer = Trainer()
+    # --data_dir: an .npz of decoded images (data.ArrayBuilder.from_npz), else synthetic tensors
+    builder = None
+    if FLAGS.data_dir:
+        from . import data as data_lib
+        path = FLAGS.data_dir if os.path.isfile(FLAGS.data_dir) else os.path.join(FLAGS.data_dir, FLAGS.dataset + '.npz')
+        builder = data_lib.ArrayBuilder.from_npz(path)
+        builder.download_and_prepare()
+        trainer = Trainer(num_classes=builder.info.features['label'].num_classes,
+                          num_examples=builder.info.splits[FLAGS.train_split].num_examples)
+    else:
+        trainer = Trainer()
     R = trainer.strategy.num_replicas_in_sync
     dev = trainer.engine.device
     num_train_examples, num_classes = trainer.num_examples, trainer.num_classes
-    num_eval_examples = FLAGS.b200_num_eval_examples
+    num_eval_examples = (builder.info.splits[FLAGS.eval_split].num_examples if builder is not None
+                         else FLAGS.b200_num_eval_examples)
     train_steps = model_lib.get_train_steps(num_train_examples)
     eval_steps = FLAGS.eval_steps or int(math.ceil(num_eval_examples / FLAGS.eval_batch_size))
     epoch_steps = int(round(num_train_examples / FLAGS.train_batch_size))
@@ -342,7 +353,13 @@ def main(argv):
     logging.info('# eval examples: %d', num_eval_examples)
     logging.info('# eval steps: %d', eval_steps)
     assert FLAGS.eval_batch_size % R == 0 and FLAGS.train_batch_size % R == 0
-    eval_fn = lambda i: synthetic_eval_batch(FLAGS.eval_batch_size // R, FLAGS.image_size, num_classes, dev, 99991 * (rank + 1) + i)
+    if builder is not None:
+        def eval_fn(i, _it=[None]):
+            if i == 0 or _it[0] is None:
+                _it[0] = data_lib.build_distributed_dataset(builder, FLAGS.eval_batch_size, False, trainer.strategy, None)
+            return next(_it[0])
+    else:
+        eval_fn = lambda i: synthetic_eval_batch(FLAGS.eval_batch_size // R, FLAGS.image_size, num_classes, dev, 99991 * (rank + 1) + i)
 
     if FLAGS.mode == 'eval':
         manager = ckpt_lib.CheckpointManager(trainer.model, None, FLAGS.model_dir)
@@ -370,10 +387,14 @@ def main(argv):
     manager = ckpt_lib.try_restore_from_checkpoint(trainer.model, trainer.optimizer) if FLAGS.model_dir else None
     steps_per_loop = max(1, checkpoint_steps)
     cur_step = trainer.optimizer.iterations
+    iterator = (data_lib.build_distributed_dataset(builder, FLAGS.train_batch_size, True, trainer.strategy, None)
+                if builder is not None else None)
     while cur_step < train_steps:
         for _ in range(min(steps_per_loop, train_steps - cur_step)):
             seed = 1234 + rank + 7919 * cur_step
-            if pretrain:
+            if iterator is not None:
+                features, labels = next(iterator)
+            elif pretrain:
                 features, labels = synthetic_batch(B, FLAGS.image_size, num_classes, dev, seed)
             else:
                 features, labels = synthetic_eval_batch(B, FLAGS.image_size, num_classes, dev, seed)

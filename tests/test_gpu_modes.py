@@ -169,3 +169,32 @@ def test_train_then_eval_driver(flags, tmp_path):
     engine.set_engine(None)
     run.main(['run'])
     assert os.path.exists(os.path.join(md, 'ckpt-6.npz'))
+
+
+def test_preprocess_for_eval_and_input_pipeline(flags):
+    """`preprocess_for_eval` (central crop 0.875 + bicubic resize + clip, tf2/data_util.py:175-243,478-494) against the
+    oracle, and the array-backed `tf2/data.py` pipeline end to end on the device."""
+    import numpy as np
+    from oracle import data_util as OD
+    from simclr_b200 import data_util as DU, data as D, engine, flags_def
+    engine.set_engine(engine.Engine(precision='bf16', conv_engine='tc'))
+    g = torch.Generator().manual_seed(5)
+    images = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, generator=g) for h, w in ((96, 128), (130, 90), (64, 64), (75, 201))]
+    ref = torch.stack([OD.preprocess_for_eval(im.double() / 255.0, 64, 64) for im in images])
+    out = DU.preprocess_for_eval_batch(images, 64, 64)
+    assert (out.cpu().double() - ref).abs().max() < 2e-5
+    for im in images:
+        assert DU.center_crop_box(im.shape[0], im.shape[1], 64, 64) == OD.center_crop_box(im.shape[0], im.shape[1], 64, 64)
+    same = DU.preprocess_image(images[2], 64, 64, is_training=False, test_crop=False)      # CIFAR-style: no crop
+    assert (same.cpu() - images[2].float() / 255.0).abs().max() < 1e-6
+    # pipeline: two views per sample for pretraining, one centre crop for eval
+    flags_def.set_flags(image_size=32, train_mode='pretrain', train_split='train', eval_split='validation')
+    arr = np.random.RandomState(0).randint(0, 256, (40, 48, 56, 3), dtype=np.uint8)
+    b = D.ArrayBuilder({'train': (arr, np.arange(40) % 10), 'validation': (arr[:10], np.arange(10) % 10)}, 10)
+    it = D.build_input_fn(b, 16, None, True)(D.InputContext(1, 0, 1), seed=3)
+    f, lab = next(it)
+    assert f.shape == (16, 32, 32, 6) and f.dtype == torch.float32 and f.is_cuda and lab.shape == (16, 10)
+    assert float(f.min()) >= 0.0 and float(f.max()) <= 1.0 and not torch.equal(f[..., :3], f[..., 3:])
+    assert torch.equal(lab.sum(1), torch.ones(16, device='cuda'))
+    fe, le = next(D.build_input_fn(b, 8, None, False)(D.InputContext(1, 0, 1)))
+    assert fe.shape == (8, 32, 32, 3) and torch.equal(le.argmax(1).cpu(), torch.arange(8) % 10)

@@ -278,3 +278,37 @@ def test_checkpoint_manager_roundtrip(tmp_path):
     m3 = FakeModel(); m3.variables[1].value.zero_()
     assert C.CheckpointManager(m3, None, str(tmp_path)).restore(mgr.latest_checkpoint, weights_only=True) == 0
     assert float(m3.variables[1].value[0]) == 30.0
+
+
+def test_input_pipeline_host_logic(tmp_path):
+    """tf2/data.py:29-98 over an ArrayBuilder: per-replica batch size, per-pipeline shards, shuffle buffer + repeat +
+    drop_remainder when training, one ordered pass with a ragged last batch otherwise, npz round trip."""
+    import numpy as np
+    from simclr_b200 import data as D, flags_def
+    F = flags_def.FLAGS
+    if not F.is_parsed():
+        F(['test'])
+    saved = {k: getattr(F, k) for k in ('image_size', 'train_mode', 'train_split', 'eval_split')}
+    try:
+        flags_def.set_flags(image_size=64, train_mode='pretrain', train_split='train', eval_split='validation')
+        imgs = np.zeros((50, 8, 8, 3), dtype=np.uint8)
+        path = str(tmp_path / 'toy.npz')
+        np.savez(path, train_images=imgs, train_labels=np.arange(50) % 5, validation_images=imgs[:11],
+                 validation_labels=np.arange(11) % 5, num_classes=5)
+        b = D.ArrayBuilder.from_npz(path)
+        assert b.info.splits['train'].num_examples == 50 and b.info.features['label'].num_classes == 5
+        fake = lambda e, idx: list(idx)
+        ctx0, ctx1 = D.InputContext(2, 0, 2), D.InputContext(2, 1, 2)
+        it0 = D.build_input_fn(b, 8, None, True)(ctx0, seed=1, make_batch=fake)
+        it1 = D.build_input_fn(b, 8, None, True)(ctx1, seed=1, make_batch=fake)
+        a = [next(it0) for _ in range(20)]; c = [next(it1) for _ in range(20)]
+        assert all(len(x) == 4 for x in a + c)                                  # 8 global / 2 replicas
+        assert set(sum(a, [])) <= set(range(0, 25)) and set(sum(c, [])) <= set(range(25, 50))   # disjoint shards
+        assert set(sum(a, [])) == set(range(0, 25))                             # repeat(-1): every example comes around
+        assert sum(a, [])[:25] != list(range(25))                               # shuffled (buffer of 40 > shard)
+        ev = list(D.build_input_fn(b, 8, None, False)(D.InputContext(1, 0, 1), make_batch=fake))
+        assert [len(x) for x in ev] == [8, 3] and sum(ev, []) == list(range(11))   # ordered, ragged last batch kept
+        with pytest.raises(ValueError):
+            D.build_input_fn(b, 9, None, True)(ctx0, make_batch=fake)
+    finally:
+        flags_def.set_flags(**saved)
