@@ -251,12 +251,23 @@ def run_b200(args):
         time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    comm = trainer.strategy.comm if world > 1 else None
+    wait0 = comm.wait_ns() if comm is not None else 0
     ev0.record()
     for _ in range(args.steps):
         loss = step_fn()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    # per-rank slack: time spent inside the SyncBN / all-gather kernels waiting for the peers' contributions.  The
+    # slowest GPU of the step waits ~0 ms, the others wait for it: min over ranks = cost of the exchanges themselves,
+    # max - min = GPU-to-GPU speed spread (power capping) that lock-step data parallelism cannot hide.
+    sync_wait = None
+    if comm is not None:
+        w = torch.tensor([(comm.wait_ns() - wait0) / 1e6 / args.steps], device=eng.device)
+        allw = [torch.zeros_like(w) for _ in range(world)]
+        dist.all_gather(allw, w)
+        sync_wait = [round(float(x.item()), 3) for x in allw]
     if sampler:
         sampler.stop_flag = True
         sampler.join(2)
@@ -268,7 +279,7 @@ def run_b200(args):
     ips = B * world * args.steps / (ms / 1e3)
     loss_val = float(loss)
 
-    log('timed region done: %.2f ms/step' % ms_per_step)
+    log('timed region done: %.2f ms/step' % ms_per_step + ('' if sync_wait is None else ' peer-wait ms/step per rank %s' % sync_wait))
     # ---- e2e: host buffers, H2D inside the timed region, D2H of the loss ------
     host_f = [torch.rand(B, S, S, 6).pin_memory() for _ in range(2)]
     host_l = [labels.cpu().pin_memory() for _ in range(2)]
@@ -423,6 +434,7 @@ def run_b200(args):
                        'collectives': ('none' if world == 1 else ('nvlink peer-memory kernels (SyncBN, all-gathers) + NCCL gradient all-reduce' if peer else 'NCCL'))},
             'e2e': {'value': e2e_ips, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches_per_step * args.steps,
+            'peer_wait_ms_per_step_by_rank': sync_wait,
             'clocks': sampler.summary() if sampler else None,
             'roofline': roof, 'cpu_baseline': cpu, 'loss': loss_val,
             'fp32_accurate_tensor_core_mode': secondary,

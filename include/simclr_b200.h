@@ -188,16 +188,36 @@ SIMCLR_API int simclr_bn_bwd_apply_coef(const void* dz, int dtype, const void* y
                                         int dy_dtype, int64_t rows, int64_t C, const float* coef,
                                         const float* mask_scale, const float* mask_shift, void* stream);
 
+/* Tail of a PROJECTION block (tf2/resnet.py:342-353,415-423 + :382,:487) with the shortcut's BatchNorm folded in:
+ *   forward  z = relu(scale*y + shift + round(scale2*y2 + shift2))   (y2: the shortcut conv's output; its BN output
+ *            is rounded to the activation type as the separate kernel would have stored it, but never stored),
+ *            one ReLU bit per element like simclr_bn_apply_relu_mask;
+ *   backward dz <- (dz + dz2) * mask in place, sums of both BatchNorms in the same pass (sums2 [2][C] w.r.t. y2,
+ *            mean2, rstd2), then dy = coef*(dz, y, 1) and dy2 = coef2*(dz, y2, 1) in one pass over dz.
+ * fp32/fp32 or bf16/bf16 tensors. */
+SIMCLR_API int simclr_bn_apply2_relu_mask(const void* y, const void* y2, int y_dtype, void* z, int z_dtype,
+                                          int64_t rows, int64_t C, const float* scale, const float* shift,
+                                          const float* scale2, const float* shift2, uint8_t* relu_mask_bits,
+                                          void* stream);
+SIMCLR_API int simclr_bn_bwd_reduce2_bits(void* dz, const void* dz2, const uint8_t* relu_mask_bits, int dtype,
+                                          const void* y, const void* y2, int y_dtype, int64_t rows, int64_t C,
+                                          const float* mean, const float* rstd, const float* mean2,
+                                          const float* rstd2, double* sums, double* sums2, void* stream);
+SIMCLR_API int simclr_bn_bwd_apply2_coef(const void* dz, int dtype, const void* y, const void* y2, int y_dtype,
+                                         void* dy, void* dy2, int dy_dtype, int64_t rows, int64_t C,
+                                         const float* coef, const float* coef2, void* stream);
+
 /* The stem's BatchNorm + ReLU + MaxPooling2D (tf2/resnet.py:593-611) without materialising the BN output:
  * forward pools relu(scale*y + shift) of the conv output y directly (same rounding as the unfused chain);
  * backward forms dz = maxpool_bwd(d [+ d2]) * [scale*y + shift > 0] on the fly, first for the BatchNorm
  * reduction (sums [2][C] = (sum dz, sum dz*xhat)), then for dy = coef0*dz + coef1*y + coef2.
- * C/8 (bf16; C/4 fp32) must divide 256. */
+ * C/8 (bf16; C/4 fp32) must divide 256.  bf16 only, optional: `ysel` [N,Ho,Wo,C] = y at each window's argmax,
+ * written by the forward; given to the reduction it replaces the pass over y by one over the pooled tensors. */
 SIMCLR_API int simclr_bn_relu_maxpool_fwd(const void* y, int dtype, const float* scale, const float* shift,
-                                          void* out, uint8_t* argmax, int64_t N, int64_t H, int64_t W, int64_t C,
-                                          void* stream);
+                                          void* out, uint8_t* argmax, void* ysel, int64_t N, int64_t H, int64_t W,
+                                          int64_t C, void* stream);
 SIMCLR_API int simclr_maxpool_bn_bwd_reduce(const void* d, const void* d2, const uint8_t* argmax, const void* y,
-                                            int dtype, int64_t N, int64_t H, int64_t W, int64_t C,
+                                            const void* ysel, int dtype, int64_t N, int64_t H, int64_t W, int64_t C,
                                             const float* mean, const float* rstd, const float* scale,
                                             const float* shift, double* sums, void* stream);
 SIMCLR_API int simclr_maxpool_bn_bwd_apply(const void* d, const void* d2, const uint8_t* argmax, const void* y,
@@ -373,9 +393,10 @@ SIMCLR_API int simclr_adam_apply(float* w, const float* g, float* m, float* v, i
  * paths).  Every rank owns one allocation of identical layout that all peers have
  * mapped ("symmetric memory"); `peer_bufs_dev` is a DEVICE array of `world` base pointers (entry
  * `rank` is the local one), the remaining arguments are byte offsets into that allocation, the
- * same on every rank.  `seq_dev` is a device uint64 (initialised to 1, identical on every rank)
- * that the kernel advances by one per call: the calls are CUDA-graph capturable and must be issued
- * in the same order on every rank.  A peer that does not show up within 20 s traps the kernel.
+ * same on every rank.  `seq_dev` points to TWO device uint64: [0] the sequence number (initialised to 1,
+ * identical on every rank) that the kernel advances by one per call, [1] a counter (initialise to 0) to which
+ * the kernel adds the nanoseconds this rank spent waiting for its peers -- per-rank slack, reported by
+ * bench.py.  The calls are CUDA-graph capturable and must be issued in the same order on every rank.  A peer that does not show up within 20 s traps the kernel.
  *
  * SyncBatchNormalization (tf2/resnet.py:54-60): sums [2][C] doubles of THIS replica ->
  * one-shot exchange (region data_off + ((seq % nslot)*world + rank)*slot_bytes of every peer,

@@ -50,8 +50,9 @@ class PeerComm:
         self.peers_dev = int(self.handle.buffer_ptrs_dev)
         self.buf.zero_()
         # sequence numbers (start at 1: flag words start at 0) and CTA arrival counters, local memory
-        self.bn_seq = torch.ones(1, dtype=torch.int64, device=device)
-        self.gather_seq = {n: torch.ones(1, dtype=torch.int64, device=device) for n in GATHER_CHANNELS}
+        # [sequence, nanoseconds spent waiting for peers] per channel
+        self.bn_seq = torch.tensor([1, 0], dtype=torch.int64, device=device)
+        self.gather_seq = {n: torch.tensor([1, 0], dtype=torch.int64, device=device) for n in GATHER_CHANNELS}
         self.gather_arrive = {n: torch.zeros(1, dtype=torch.int32, device=device) for n in GATHER_CHANNELS}
         torch.cuda.synchronize(device)
         dist.barrier(self.group)             # nobody pushes before every buffer is zeroed
@@ -72,6 +73,11 @@ class PeerComm:
             import warnings
             warnings.warn('simclr_b200: peer-memory collectives unavailable (%r); using NCCL' % (exc,))
             return None
+
+    def wait_ns(self):
+        """Nanoseconds this rank has spent inside the exchange kernels waiting for its peers, since creation
+        (device counters: a synchronising read).  The slowest rank of a step waits ~0; the others wait for it."""
+        return int(self.bn_seq[1].item()) + sum(int(t[1].item()) for t in self.gather_seq.values())
 
     # -- fused SyncBN exchanges ----------------------------------------------------
     def _bn_args(self):

@@ -57,17 +57,23 @@ inline RedLayout red_layout(int64_t C) {
 // zmask = shift, both fp32 [C]); dz is neither re-read from a mask tensor nor written.
 // mode 3: mode 1 with the ReLU mask of the block tail as ONE BIT per element (byte i = the 8 channels
 // of 16-byte vector i, written by bn_apply_kernel) instead of the output tensor z: 1/16 of the bytes.
+// mode 4: mode 3 for the tail of a PROJECTION block: the masked gradient is also the gradient w.r.t. the
+// output of the shortcut's BatchNorm (no ReLU), whose reduction (conv output y2, mean2, rstd2 -> sums2) is
+// taken in the same pass instead of re-reading the gradient.
 // The kernels are HBM-latency bound: each thread keeps 4 (modes 0, 2) or 2 (mode 1) rows of
 // 16-byte loads in flight, two 256-thread CTAs per SM.
 template <typename T, typename Ty, int MODE>
 __global__ void __launch_bounds__(BT, 2)
 bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __restrict__ zmask_,
                  const Ty* __restrict__ y, int64_t rows, int C, int P, int rows_per_block,
-                 const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ sums) {
+                 const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ sums,
+                 const Ty* __restrict__ y2 = nullptr, const float* __restrict__ mean2 = nullptr,
+                 const float* __restrict__ rstd2 = nullptr, double* __restrict__ sums2 = nullptr) {
   extern __shared__ double sh[];  // [row_lanes][P*8][2]
+  constexpr bool BITS = MODE == 3 || MODE == 4;      // mode 4: mode 3 for a projection block, see below
   const T* __restrict__ a2 = MODE == 2 ? nullptr : (const T*)a2_;
-  const T* __restrict__ zmask = (MODE == 2 || MODE == 3) ? nullptr : (const T*)zmask_;
-  const uint8_t* __restrict__ zbits = MODE == 3 ? (const uint8_t*)zmask_ : nullptr;
+  const T* __restrict__ zmask = (MODE == 2 || BITS) ? nullptr : (const T*)zmask_;
+  const uint8_t* __restrict__ zbits = BITS ? (const uint8_t*)zmask_ : nullptr;
   const int tx = threadIdx.x % P, ty = threadIdx.x / P;
   const int row_lanes = BT / P;
   const int cvecs = C / 8;
@@ -79,13 +85,17 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
     // Per-thread sums are fp32 (a few hundred rows at most), everything from the block tree on is fp64.  The
     // forward statistics (mode 0) additionally fold into fp64 every few groups; doing that in the backward
     // modes costs ~13% of their bandwidth (fp32->fp64 converts are slow) for no measurable accuracy.
-    float s0[8], s1[8];
-    double d0[8], d1[8];
+    float s0[8], s1[8], s2[8];
+    double d0[8], d1[8], d2[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = 0.f; d0[i] = d1[i] = 0.0; }
+    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = s2[i] = 0.f; d0[i] = d1[i] = d2[i] = 0.0; }
     auto fold = [&]() {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { d0[i] += (double)s0[i]; d1[i] += (double)s1[i]; s0[i] = 0.f; s1[i] = 0.f; }
+      if (MODE == 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { d2[i] += (double)s2[i]; s2[i] = 0.f; }
+      }
     };
     int groups = 0;
     auto fold_some = [&]() { if ((++groups & 3) == 0) fold(); };   // every 4th group: fp32->fp64 converts are slow
@@ -147,11 +157,12 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
 #pragma unroll
         for (int i = 0; i < 8; ++i) d1[i] *= (double)rstd[cv * 8 + i];
       } else {
-        float mu[8];
+        float mu[8], mu2[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mu[i] = mean[cv * 8 + i];
+        for (int i = 0; i < 8; ++i) { mu[i] = mean[cv * 8 + i]; mu2[i] = MODE == 4 ? mean2[cv * 8 + i] : 0.f; }
         const bool has2 = a2 != nullptr, hasz = zmask != nullptr;
-        auto acc = [&](int64_t off, const Raw8<T>& qv, const Raw8<T>& qw, const Raw8<T>& qz, const Raw8<Ty>& qy, unsigned bits) {
+        auto acc = [&](int64_t off, const Raw8<T>& qv, const Raw8<T>& qw, const Raw8<T>& qz, const Raw8<Ty>& qy, unsigned bits,
+                       const Raw8<Ty>& qy2) {
           float v[8], yy[8]; qv.to(v); qy.to(yy);
           if (has2) {
             float w[8]; qw.to(w);
@@ -163,11 +174,11 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = (z[i] > 0.f) ? v[i] : 0.f;
           }
-          if (MODE == 3) {
+          if (BITS) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = ((bits >> i) & 1u) ? v[i] : 0.f;
           }
-          if (has2 || hasz || MODE == 3) {
+          if (has2 || hasz || BITS) {
             store8<T>(a + off, v);
             // keep the sums consistent with what phase 2 will read back
             if (sizeof(T) == 2) {
@@ -177,34 +188,45 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) { s0[i] += v[i]; s1[i] = fmaf(v[i], yy[i] - mu[i], s1[i]); }
+          if (MODE == 4) {
+            float y2v[8]; qy2.to(y2v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s2[i] = fmaf(v[i], y2v[i] - mu2[i], s2[i]);
+          }
         };
         for (; r + row_lanes < r1; r += 2 * row_lanes) {
           const int64_t off = r * C + (int64_t)cv * 8;
-          Raw8<T> qv[2], qw[2], qz[2]; Raw8<Ty> qy[2]; unsigned qb[2] = {0u, 0u};
+          Raw8<T> qv[2], qw[2], qz[2]; Raw8<Ty> qy[2], qy2[2]; unsigned qb[2] = {0u, 0u};
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             qv[u].ld(a + off + u * lane_step);
             if (has2) qw[u].ld(a2 + off + u * lane_step); else qw[u] = qv[u];
             if (hasz) qz[u].ld(zmask + off + u * lane_step); else qz[u] = qv[u];
-            if (MODE == 3) qb[u] = zbits[(off + u * lane_step) >> 3];
+            if (BITS) qb[u] = zbits[(off + u * lane_step) >> 3];
             qy[u].ld(y + off + u * lane_step);
+            if (MODE == 4) qy2[u].ld(y2 + off + u * lane_step); else qy2[u] = qy[u];
           }
 #pragma unroll
-          for (int u = 0; u < 2; ++u) acc(off + u * lane_step, qv[u], qw[u], qz[u], qy[u], qb[u]);
+          for (int u = 0; u < 2; ++u) acc(off + u * lane_step, qv[u], qw[u], qz[u], qy[u], qb[u], qy2[u]);
         }
         for (; r < r1; r += row_lanes) {
           const int64_t off = r * C + (int64_t)cv * 8;
-          Raw8<T> qv, qw, qz; Raw8<Ty> qy;
+          Raw8<T> qv, qw, qz; Raw8<Ty> qy, qy2;
           qv.ld(a + off);
           if (has2) qw.ld(a2 + off); else qw = qv;
           if (hasz) qz.ld(zmask + off); else qz = qv;
-          const unsigned qb = MODE == 3 ? (unsigned)zbits[off >> 3] : 0u;
+          const unsigned qb = BITS ? (unsigned)zbits[off >> 3] : 0u;
           qy.ld(y + off);
-          acc(off, qv, qw, qz, qy, qb);
+          if (MODE == 4) qy2.ld(y2 + off); else qy2 = qy;
+          acc(off, qv, qw, qz, qy, qb, qy2);
         }
         fold();
 #pragma unroll
         for (int i = 0; i < 8; ++i) d1[i] *= (double)rstd[cv * 8 + i];
+        if (MODE == 4) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d2[i] *= (double)rstd2[cv * 8 + i];
+        }
       }
     }
     // block tree over row lanes
@@ -233,6 +255,20 @@ bn_reduce_kernel(T* __restrict__ a, const void* __restrict__ a2_, const void* __
         }
       }
       atomicAdd(&sums[(e >> 3) * C + ch], acc);
+    }
+    if (MODE == 4) {        // second tree: (sum dz, sum dz*xhat2) of the shortcut's BatchNorm
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mine[8 + i] = d2[i];
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < P * 16; idx += BT) {
+        const int px = idx / 16, e = idx % 16;
+        const int c8 = (cv - tx + px);
+        if (c8 >= cvecs) continue;
+        double acc = 0.0;
+        for (int l = 0; l < row_lanes; ++l) acc += sh[((size_t)l * P + px) * 16 + e];
+        atomicAdd(&sums2[(e >> 3) * C + c8 * 8 + (e & 7)], acc);
+      }
     }
   }
 }
@@ -371,6 +407,94 @@ bn_bwd_apply_kernel(const T* __restrict__ dz, const Ty* __restrict__ y, Td* __re
   }
 }
 
+// Tail of a PROJECTION block in one pass: z = relu(scale*y + shift + zs) with zs = the shortcut's BatchNorm output
+// scale2*y2 + shift2 rounded to the activation type exactly as the unfused chain would have stored it -- which
+// it now never is.  Writes the ReLU bit mask like bn_apply_kernel.
+template <typename Ty, typename Tz>
+__global__ void __launch_bounds__(BT)
+bn_apply2_tail_kernel(const Ty* __restrict__ y, const Ty* __restrict__ y2, Tz* __restrict__ z, int64_t nvec, int C,
+                      const float* __restrict__ scale, const float* __restrict__ shift,
+                      const float* __restrict__ scale2, const float* __restrict__ shift2,
+                      uint8_t* __restrict__ mask_bits) {
+  const int64_t stride = (int64_t)gridDim.x * BT;
+  int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
+  const bool fixed_c = (stride * 8) % C == 0;
+  float sc[8], sh[8], sc2[8], sh2[8];
+  auto load_coef = [&](int c) {
+    load8<float>(scale + c, sc); load8<float>(shift + c, sh); load8<float>(scale2 + c, sc2); load8<float>(shift2 + c, sh2);
+  };
+  if (fixed_c) load_coef((int)((i * 8) % C));
+  auto body = [&](int64_t off, const Raw8<Ty>& qy, const Raw8<Ty>& qy2) {
+    float v[8], w[8]; qy.to(v); qy2.to(w);
+    unsigned b = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float zs = to_f<Tz>(from_f<Tz>(fmaf(w[k], sc2[k], sh2[k])));
+      v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]) + zs, 0.f);
+      b |= (to_f<Tz>(from_f<Tz>(v[k])) > 0.f ? 1u : 0u) << k;
+    }
+    store8<Tz>(z + off, v);
+    mask_bits[off >> 3] = (uint8_t)b;
+  };
+  if (fixed_c) {
+    for (; i + stride < nvec; i += 2 * stride) {
+      const int64_t o0 = i * 8, o1 = (i + stride) * 8;
+      Raw8<Ty> q0, q1, r0, r1;
+      q0.ld(y + o0); q1.ld(y + o1); r0.ld(y2 + o0); r1.ld(y2 + o1);
+      body(o0, q0, r0); body(o1, q1, r1);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    const int64_t off = i * 8;
+    if (!fixed_c) load_coef((int)(off % C));
+    Raw8<Ty> q, r; q.ld(y + off); r.ld(y2 + off);
+    body(off, q, r);
+  }
+}
+
+// Backward of the same tail: the masked gradient dz feeds two BatchNorms (the block's last one and the shortcut's);
+// dy = k1*dz + k2*y + k3 and dy2 = m1*dz + m2*y2 + m3 in one pass over dz.
+template <typename T, typename Ty, typename Td>
+__global__ void __launch_bounds__(BT, 2)       // 48 coefficient registers per thread: no 64-register cap here
+bn_bwd_apply2_kernel(const T* __restrict__ dz, const Ty* __restrict__ y, const Ty* __restrict__ y2, Td* __restrict__ dy,
+                     Td* __restrict__ dy2, int64_t nvec, int C, const float* __restrict__ coef,
+                     const float* __restrict__ coef2) {
+  const int64_t stride = (int64_t)gridDim.x * BT;
+  int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
+  const bool fixed_c = (stride * 8) % C == 0;
+  float k1[8], k2[8], k3[8], m1[8], m2[8], m3[8];
+  auto load_coef = [&](int c) {
+    load8<float>(coef + c, k1); load8<float>(coef + C + c, k2); load8<float>(coef + 2 * C + c, k3);
+    load8<float>(coef2 + c, m1); load8<float>(coef2 + C + c, m2); load8<float>(coef2 + 2 * C + c, m3);
+  };
+  if (fixed_c) load_coef((int)((i * 8) % C));
+  auto body = [&](int64_t off, const Raw8<T>& qg, const Raw8<Ty>& qy, const Raw8<Ty>& qy2) {
+    float g[8], a[8], o[8]; qg.to(g); qy.to(a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(k1[k], g[k], fmaf(k2[k], a[k], k3[k]));
+    store8<Td>(dy + off, o);
+    qy2.to(a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(m1[k], g[k], fmaf(m2[k], a[k], m3[k]));
+    store8<Td>(dy2 + off, o);
+  };
+  if (fixed_c) {
+    for (; i + stride < nvec; i += 2 * stride) {
+      const int64_t o0 = i * 8, o1 = (i + stride) * 8;
+      Raw8<T> g0, g1; Raw8<Ty> a0, a1, b0, b1;
+      g0.ld(dz + o0); g1.ld(dz + o1); a0.ld(y + o0); a1.ld(y + o1); b0.ld(y2 + o0); b1.ld(y2 + o1);
+      body(o0, g0, a0, b0); body(o1, g1, a1, b1);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    const int64_t off = i * 8;
+    if (!fixed_c) load_coef((int)(off % C));
+    Raw8<T> qg; Raw8<Ty> qy, qy2;
+    qg.ld(dz + off); qy.ld(y + off); qy2.ld(y2 + off);
+    body(off, qg, qy, qy2);
+  }
+}
+
 // grid for the element-wise kernels: as many CTAs as fit, rounded down so that gridDim*BT*8 is a
 // multiple of C (see bn_apply_kernel)
 inline unsigned ew_grid_c(int64_t nvec, int64_t C) {
@@ -388,7 +512,8 @@ inline unsigned ew_grid_c(int64_t nvec, int64_t C) {
 
 template <typename T, typename Ty, int MODE>
 int launch_reduce(void* a, const void* a2, const void* zmask, const void* y, int64_t rows, int64_t C,
-                  const float* mean, const float* rstd, double* sums, cudaStream_t st) {
+                  const float* mean, const float* rstd, double* sums, cudaStream_t st, const void* y2 = nullptr,
+                  const float* mean2 = nullptr, const float* rstd2 = nullptr, double* sums2 = nullptr) {
   const RedLayout l = red_layout(C);
   int64_t nblocks = (rows + l.row_lanes * 8 - 1) / (l.row_lanes * 8);
   // 2 CTAs of 256 threads are resident per SM (__launch_bounds__(BT, 2)): one wave of fat blocks.  Every block ends
@@ -403,9 +528,13 @@ int launch_reduce(void* a, const void* a2, const void* zmask, const void* y, int
   if (!accumulate_prezeroed()) {
     cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st);
     if (e != cudaSuccess) { set_error("bn reduce memset: %s", cudaGetErrorString(e)); return (int)e; }
+    if (sums2) {
+      e = cudaMemsetAsync(sums2, 0, 2 * C * sizeof(double), st);
+      if (e != cudaSuccess) { set_error("bn reduce memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
   }
   bn_reduce_kernel<T, Ty, MODE><<<(unsigned)nblocks, BT, smem, st>>>(
-      (T*)a, a2, zmask, (const Ty*)y, rows, (int)C, l.P, rows_per_block, mean, rstd, sums);
+      (T*)a, a2, zmask, (const Ty*)y, rows, (int)C, l.P, rows_per_block, mean, rstd, sums, (const Ty*)y2, mean2, rstd2, sums2);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }
@@ -592,6 +721,58 @@ int simclr_bn_bwd_apply_coef(const void* dz, int dtype, const void* y, int y_dty
   SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_bwd_apply_coef: bad shape");
   SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(y) && aligned16(dy) && aligned16(coef), "bn_bwd_apply_coef: alignment");
   return launch_bwd_apply(dz, dtype, y, y_dtype, dy, dy_dtype, rows, C, coef, mask_scale, mask_shift, (cudaStream_t)stream);
+}
+
+/* Projection-block tail (see bn_apply2_tail_kernel / bn_reduce_kernel mode 4 / bn_bwd_apply2_kernel). */
+int simclr_bn_apply2_relu_mask(const void* y, const void* y2, int y_dtype, void* z, int z_dtype, int64_t rows, int64_t C,
+                               const float* scale, const float* shift, const float* scale2, const float* shift2,
+                               uint8_t* relu_mask_bits, void* stream) {
+  SIMCLR_CHECK_ARG(y && y2 && z && scale && shift && scale2 && shift2 && relu_mask_bits, "bn_apply2_relu_mask: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_apply2_relu_mask: need rows>0 and C%%8==0");
+  SIMCLR_CHECK_ARG(aligned16(y) && aligned16(y2) && aligned16(z), "bn_apply2_relu_mask: pointers must be 16-byte aligned");
+  const int64_t nvec = rows * C / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = ew_grid_c(nvec, C);
+  if (y_dtype == SIMCLR_F32 && z_dtype == SIMCLR_F32)
+    bn_apply2_tail_kernel<float, float><<<grid, BT, 0, st>>>((const float*)y, (const float*)y2, (float*)z, nvec, (int)C, scale, shift, scale2, shift2, relu_mask_bits);
+  else if (y_dtype == SIMCLR_BF16 && z_dtype == SIMCLR_BF16)
+    bn_apply2_tail_kernel<bf16, bf16><<<grid, BT, 0, st>>>((const bf16*)y, (const bf16*)y2, (bf16*)z, nvec, (int)C, scale, shift, scale2, shift2, relu_mask_bits);
+  else { set_error("bn_apply2_relu_mask: unsupported dtypes %d/%d", y_dtype, z_dtype); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
+}
+
+int simclr_bn_bwd_reduce2_bits(void* dz, const void* dz2, const uint8_t* relu_mask_bits, int dtype, const void* y,
+                               const void* y2, int y_dtype, int64_t rows, int64_t C, const float* mean,
+                               const float* rstd, const float* mean2, const float* rstd2, double* sums, double* sums2,
+                               void* stream) {
+  SIMCLR_CHECK_ARG(dz && relu_mask_bits && y && y2 && mean && rstd && mean2 && rstd2 && sums && sums2, "bn_bwd_reduce2_bits: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_bwd_reduce2_bits: need rows>0 and C%%8==0");
+  SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(dz2) && aligned16(y) && aligned16(y2), "bn_bwd_reduce2_bits: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SIMCLR_F32 && y_dtype == SIMCLR_F32)
+    return launch_reduce<float, float, 4>(dz, dz2, relu_mask_bits, y, rows, C, mean, rstd, sums, st, y2, mean2, rstd2, sums2);
+  if (dtype == SIMCLR_BF16 && y_dtype == SIMCLR_BF16)
+    return launch_reduce<bf16, bf16, 4>(dz, dz2, relu_mask_bits, y, rows, C, mean, rstd, sums, st, y2, mean2, rstd2, sums2);
+  set_error("bn_bwd_reduce2_bits: unsupported dtypes");
+  return SIMCLR_ERR_INVALID_ARG;
+}
+
+int simclr_bn_bwd_apply2_coef(const void* dz, int dtype, const void* y, const void* y2, int y_dtype, void* dy, void* dy2,
+                              int dy_dtype, int64_t rows, int64_t C, const float* coef, const float* coef2, void* stream) {
+  SIMCLR_CHECK_ARG(dz && y && y2 && dy && dy2 && coef && coef2, "bn_bwd_apply2_coef: null pointer");
+  SIMCLR_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_bwd_apply2_coef: bad shape");
+  SIMCLR_CHECK_ARG(aligned16(dz) && aligned16(y) && aligned16(y2) && aligned16(dy) && aligned16(dy2), "bn_bwd_apply2_coef: alignment");
+  const int64_t nvec = rows * C / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = ew_grid_c(nvec, C);
+  if (dtype == SIMCLR_F32 && y_dtype == SIMCLR_F32 && dy_dtype == SIMCLR_F32)
+    bn_bwd_apply2_kernel<float, float, float><<<grid, BT, 0, st>>>((const float*)dz, (const float*)y, (const float*)y2, (float*)dy, (float*)dy2, nvec, (int)C, coef, coef2);
+  else if (dtype == SIMCLR_BF16 && y_dtype == SIMCLR_BF16 && dy_dtype == SIMCLR_BF16)
+    bn_bwd_apply2_kernel<bf16, bf16, bf16><<<grid, BT, 0, st>>>((const bf16*)dz, (const bf16*)y, (const bf16*)y2, (bf16*)dy, (bf16*)dy2, nvec, (int)C, coef, coef2);
+  else { set_error("bn_bwd_apply2_coef: unsupported dtypes"); return SIMCLR_ERR_INVALID_ARG; }
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
 }
 
 }  // extern "C"

@@ -15,7 +15,8 @@
 // in `peers[world]`): the caller passes byte offsets.  Ordering: data stores, __threadfence_system(),
 // then a release store of the sequence number into the peer's flag word; the consumer polls its own
 // flag words with acquire loads.  Sequence numbers live in device memory and are advanced by the
-// kernels themselves, so the step can be captured in a CUDA graph and replayed.  Every spin is
+// kernels themselves, so the step can be captured in a CUDA graph and replayed; the word after each
+// sequence number accumulates the nanoseconds this rank spent waiting for its peers.  Every spin is
 // bounded: a protocol error traps after SPIN_TIMEOUT_NS instead of hanging the GPU.
 #include "common.cuh"
 
@@ -58,7 +59,8 @@ struct Peers {
 // CTA barrier) with all `world` regions of the local slot complete.  `slot_doubles` = capacity of a region.
 __device__ __forceinline__ const double* exchange_doubles(const Peers& P, const double* __restrict__ local, int n,
                                                           long long data_off, long long flag_off, int nslot,
-                                                          long long slot_doubles, unsigned long long seq) {
+                                                          long long slot_doubles, unsigned long long seq,
+                                                          unsigned long long* __restrict__ wait_ns) {
   const int slot = (int)(seq % (unsigned long long)nslot);
   const long long region = ((long long)slot * P.world + P.rank) * slot_doubles;
   for (int r = 0; r < P.world; ++r) {
@@ -67,6 +69,7 @@ __device__ __forceinline__ const double* exchange_doubles(const Peers& P, const 
   }
   __threadfence_system();
   __syncthreads();
+  const unsigned long long t0 = threadIdx.x == 0 ? gtimer() : 0ull;
   if ((int)threadIdx.x < P.world) {
     unsigned long long* pf = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(P.bufs[threadIdx.x]) + flag_off) +
                              (long long)slot * P.world + P.rank;
@@ -76,6 +79,7 @@ __device__ __forceinline__ const double* exchange_doubles(const Peers& P, const 
     wait_flag(mine, seq, 1);
   }
   __syncthreads();
+  if (threadIdx.x == 0) *wait_ns += gtimer() - t0;      // time this rank spent waiting for its peers (bench.py reports it)
   return reinterpret_cast<const double*>(reinterpret_cast<const char*>(P.bufs[P.rank]) + data_off) +
          (long long)slot * P.world * slot_doubles;
 }
@@ -88,7 +92,7 @@ bn_finalize_sync_kernel(Peers P, const double* __restrict__ sums, double count_l
                         long long data_off, long long flag_off, int nslot, long long slot_doubles,
                         unsigned long long* __restrict__ seq_dev) {
   const unsigned long long seq = *seq_dev;
-  const double* all = exchange_doubles(P, sums, 2 * C, data_off, flag_off, nslot, slot_doubles, seq);
+  const double* all = exchange_doubles(P, sums, 2 * C, data_off, flag_off, nslot, slot_doubles, seq, seq_dev + 1);
   const double count = count_local * P.world;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double s0 = 0.0, s1 = 0.0;
@@ -118,7 +122,7 @@ bn_bwd_coef_sync_kernel(Peers P, const double* __restrict__ sums, double count_l
                         float* __restrict__ dbeta, int C, long long data_off, long long flag_off, int nslot,
                         long long slot_doubles, unsigned long long* __restrict__ seq_dev) {
   const unsigned long long seq = *seq_dev;
-  const double* all = exchange_doubles(P, sums, 2 * C, data_off, flag_off, nslot, slot_doubles, seq);
+  const double* all = exchange_doubles(P, sums, 2 * C, data_off, flag_off, nslot, slot_doubles, seq, seq_dev + 1);
   const double inv_count = 1.0 / (count_local * P.world);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double s0 = 0.0, s1 = 0.0;
@@ -158,6 +162,7 @@ all_gather_push_kernel(Peers P, const uint4* __restrict__ src, long long chunk16
   __syncthreads();
   if (!last) return;
   __threadfence_system();
+  const unsigned long long t0 = threadIdx.x == 0 ? gtimer() : 0ull;
   if ((int)threadIdx.x < P.world) {
     unsigned long long* pf = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(P.bufs[threadIdx.x]) + flag_off) + P.rank;
     st_release_sys(pf, seq);
@@ -166,7 +171,7 @@ all_gather_push_kernel(Peers P, const uint4* __restrict__ src, long long chunk16
     wait_flag(mine, seq, 2);
   }
   __syncthreads();
-  if (threadIdx.x == 0) { *arrive = 0u; *seq_dev = seq + 1; }
+  if (threadIdx.x == 0) { *arrive = 0u; *seq_dev = seq + 1; seq_dev[1] += gtimer() - t0; }
 }
 
 }  // namespace

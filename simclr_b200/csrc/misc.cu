@@ -142,17 +142,19 @@ __global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* 
   }
 }
 
-// All conv / dense layers in one launch: blockIdx.y selects the layer (table row of 10 int64:
-// w, wf, wd, R, S, Cin, Cs, Cout, Kp, Kdp), blockIdx.x strides over its elements.
-__global__ void pack_weights_multi_kernel(const long long* __restrict__ table) {
-  const long long* t = table + (long long)blockIdx.y * 10;
+// All conv / dense layers in one launch (table row of 10 int64: w, wf, wd, R, S, Cin, Cs, Cout, Kp, Kdp).  The work
+// of every layer is cut into units -- a 32x32 tile of the [K][Cout] -> [Cout][Kp] transposition (through shared
+// memory, so that both the fp32 reads and the bf16 writes are coalesced), or 1024 consecutive elements of the dgrad
+// operand wd (a row copy) -- and the units of all layers are dealt round-robin to the CTAs: layers differ in size by
+// four orders of magnitude, one-grid-row-per-layer left the launch waiting for the blocks of the largest ones.
+constexpr int PACK_MAX_LAYERS = 1024;
+__device__ __forceinline__ void pack_elementwise(const long long* t, int64_t i0, int64_t i1) {
   const float* __restrict__ w = reinterpret_cast<const float*>(t[0]);
   __nv_bfloat16* __restrict__ wf = reinterpret_cast<__nv_bfloat16*>(t[1]);
   __nv_bfloat16* __restrict__ wd = reinterpret_cast<__nv_bfloat16*>(t[2]);
   const int R = (int)t[3], S = (int)t[4], Cin = (int)t[5], Cs = (int)t[6], Cout = (int)t[7], Kp = (int)t[8], Kdp = (int)t[9];
   const int64_t nf = (int64_t)Cout * Kp;
-  const int64_t nd = wd ? (int64_t)Cin * Kdp : 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     if (i < nf) {
       const int co = (int)(i / Kp), k = (int)(i % Kp);
       const int tap = k / Cs, c = k % Cs;
@@ -169,6 +171,66 @@ __global__ void pack_weights_multi_kernel(const long long* __restrict__ table) {
       const int ci = (int)(j / Kdp), k = (int)(j % Kdp);
       const int tap = k / Cout, co = k % Cout;
       wd[j] = __float2bfloat16_rn(tap < R * S ? w[((int64_t)tap * Cin + ci) * Cout + co] : 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const long long* __restrict__ table, int n_layers) {
+  __shared__ long long ustart[PACK_MAX_LAYERS + 1];
+  __shared__ float tile[32][33];
+  for (int l = threadIdx.x; l < n_layers; l += blockDim.x) {
+    const long long* t = table + (long long)l * 10;
+    const long long Cin = t[5], Cs = t[6], Cout = t[7], Kp = t[8], Kdp = t[9];
+    const long long nd = t[2] ? Cin * Kdp : 0;
+    long long units;
+    if (Cs == 4) units = (Cout * Kp + nd + 1023) / 1024;                    // stem layout: element-wise
+    else units = ((Kp + 31) / 32) * ((Cout + 31) / 32) + (nd + 1023) / 1024;
+    ustart[l + 1] = units;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ustart[0] = 0;
+    for (int l = 0; l < n_layers; ++l) ustart[l + 1] += ustart[l];
+  }
+  __syncthreads();
+  const long long total = ustart[n_layers];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+    int lo = 0, hi = n_layers;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ustart[mid] <= u) lo = mid; else hi = mid; }
+    const long long* t = table + (long long)lo * 10;
+    const long long local = u - ustart[lo];
+    const int R = (int)t[3], S = (int)t[4], Cin = (int)t[5], Cs = (int)t[6], Cout = (int)t[7], Kp = (int)t[8], Kdp = (int)t[9];
+    const int64_t nf = (int64_t)Cout * Kp;
+    const int64_t nd = t[2] ? (int64_t)Cin * Kdp : 0;
+    if (Cs == 4) {
+      const int64_t i0 = local * 1024;
+      pack_elementwise(t, i0, min(i0 + 1024, nf + nd));
+      continue;
+    }
+    const long long tiles_k = (Kp + 31) / 32, tiles_c = (Cout + 31) / 32;
+    if (local < tiles_k * tiles_c) {
+      const float* __restrict__ w = reinterpret_cast<const float*>(t[0]);
+      __nv_bfloat16* __restrict__ wf = reinterpret_cast<__nv_bfloat16*>(t[1]);
+      const int k0 = (int)(local % tiles_k) * 32, c0 = (int)(local / tiles_k) * 32;
+#pragma unroll
+      for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, co = c0 + tx;
+        const int tap = k / Cs, c = k % Cs;
+        float v = 0.f;
+        if (k < Kp && tap < R * S && c < Cin && co < Cout) v = w[((int64_t)tap * Cin + c) * Cout + co];
+        tile[r][tx] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = ty; r < 32; r += 8) {
+        const int co = c0 + r, k = k0 + tx;
+        if (co < Cout && k < Kp) wf[(int64_t)co * Kp + k] = __float2bfloat16_rn(tile[tx][r]);
+      }
+      __syncthreads();
+    } else {
+      const int64_t i0 = nf + (local - tiles_k * tiles_c) * 1024;
+      pack_elementwise(t, i0, min(i0 + 1024, nf + nd));
     }
   }
 }
@@ -438,8 +500,8 @@ int simclr_pack_conv_weight(const float* w_hwio, void* wf, void* wd, int dtype, 
 }
 
 int simclr_pack_conv_weights_multi(const void* table_dev, int64_t n_layers, void* stream) {
-  SIMCLR_CHECK_ARG(table_dev && n_layers > 0 && n_layers < 65536, "pack_conv_weights_multi: bad arguments");
-  pack_weights_multi_kernel<<<dim3(48, (unsigned)n_layers), 256, 0, (cudaStream_t)stream>>>((const long long*)table_dev);
+  SIMCLR_CHECK_ARG(table_dev && n_layers > 0 && n_layers <= PACK_MAX_LAYERS, "pack_conv_weights_multi: 1..%d layers", PACK_MAX_LAYERS);
+  pack_weights_multi_kernel<<<(unsigned)(num_sms() * 8), 256, 0, (cudaStream_t)stream>>>((const long long*)table_dev, (int)n_layers);
   SIMCLR_CHECK_LAUNCH();
   return SIMCLR_OK;
 }

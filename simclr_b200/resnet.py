@@ -10,6 +10,8 @@ dtype; variables are fp32 HWIO / [C] views into flat buffers.
 SK blocks (`sk_ratio > 0`, with the ResNet-D stem and shortcuts, config 5) and SE
 blocks (`se_ratio > 0`) are on the GPU path.
 """
+import os
+
 import torch
 
 from ._lib import lib, stream_ptr, F32, BF16
@@ -87,6 +89,43 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
             lib.bn_bwd_coef(mean, rstd, gam, sums_g, sums, count, coef, dgam, dbet, C, stream_ptr())
         return coef
 
+    # -- projection-block tail: this BatchNorm + the shortcut's BatchNorm + add + ReLU in one pass ------------------
+    @staticmethod
+    def tail2_enabled():
+        return os.environ.get('SIMCLR_BN_TAIL2', '1') != '0'
+
+    def forward_tail2(self, y, sums, ys, bn_s, sums_s):
+        """relu(BN(y) + BN_s(ys)) for a block with a projection shortcut (tf2/resnet.py:342-353,382; :415-423,487):
+        the shortcut's BatchNorm output is formed (and rounded) inside the kernel instead of being written and
+        re-read.  `sums` / `sums_s`: the statistics the two conv epilogues produced."""
+        e = get_engine()
+        C = self.C
+        rows = y.numel() // C
+        mean, rstd, scale, shift = self._statistics(y, True, sums)
+        mean2, rstd2, scale2, shift2 = bn_s._statistics(ys, True, sums_s)
+        z = e.empty(y.shape, y.dtype)
+        bits = e.empty((rows * C // 8,), torch.uint8)
+        lib.bn_apply2_relu_mask(y, ys, e.code(y.dtype), z, e.code(z.dtype), rows, C, scale, shift, scale2, shift2, bits,
+                                stream_ptr())
+        self.saved = ('tail2', y, ys, bits, mean, rstd, mean2, rstd2, rows, bn_s)
+        return z
+
+    def backward_tail2(self, dz, dz2=None):
+        """dz <- (dz + dz2) * relu_mask in place; returns (d conv output, d shortcut conv output)."""
+        e = get_engine()
+        _, y, ys, bits, mean, rstd, mean2, rstd2, rows, bn_s = self.saved
+        self.saved = None
+        C = self.C
+        st = stream_ptr()
+        sums, sums2 = e.sums(2 * C), e.sums(2 * C)
+        lib.bn_bwd_reduce2_bits(dz, dz2, bits, e.code(dz.dtype), y, ys, e.code(y.dtype), rows, C, mean, rstd, mean2, rstd2,
+                                sums, sums2, st)
+        coef = self._coefficients(sums, rows, mean, rstd)
+        coef2 = bn_s._coefficients(sums2, rows, mean2, rstd2)
+        dy, dys = e.empty(y.shape, e.act_dtype), e.empty(y.shape, e.act_dtype)
+        lib.bn_bwd_apply2_coef(dz, e.code(dz.dtype), y, ys, e.code(y.dtype), dy, dys, e.code(dy.dtype), rows, C, coef, coef2, st)
+        return dy, dys
+
     # -- stem: BN + ReLU + MaxPooling2D(3, 2, 'SAME') without materialising the BN output -----------------
     def forward_maxpool(self, y, sums=None):
         """Training forward of `BatchNormRelu` -> `MaxPooling2D` (tf2/resnet.py:593-611) on the conv output y
@@ -98,19 +137,21 @@ class BatchNormRelu:  # pylint: disable=missing-docstring
         Ho, Wo = (H + 1) // 2, (W + 1) // 2
         out = e.empty((N, Ho, Wo, C), y.dtype)
         argmax = e.empty((N, Ho, Wo, C), torch.uint8)
-        lib.bn_relu_maxpool_fwd(y, e.code(y.dtype), scale, shift, out, argmax, N, H, W, C, stream_ptr())
-        self.saved = ('pool', y, argmax, mean, rstd, scale, shift)
+        # bf16: y at each window's argmax, so that the backward BatchNorm reduction reads pooled-size tensors only
+        ysel = e.empty((N, Ho, Wo, C), y.dtype) if y.dtype == torch.bfloat16 else None
+        lib.bn_relu_maxpool_fwd(y, e.code(y.dtype), scale, shift, out, argmax, ysel, N, H, W, C, stream_ptr())
+        self.saved = ('pool', y, argmax, ysel, mean, rstd, scale, shift)
         return out
 
     def backward_maxpool(self, d, d2=None):
         """d (+ d2): gradient(s) w.r.t. the pooled tensor.  Returns d(conv output)."""
         e = get_engine()
-        _, y, argmax, mean, rstd, scale, shift = self.saved
+        _, y, argmax, ysel, mean, rstd, scale, shift = self.saved
         self.saved = None
         N, H, W, C = y.shape
         st = stream_ptr()
         sums = e.sums(2 * C)
-        lib.maxpool_bn_bwd_reduce(d, d2, argmax, y, e.code(y.dtype), N, H, W, C, mean, rstd, scale, shift, sums, st)
+        lib.maxpool_bn_bwd_reduce(d, d2, argmax, y, ysel, e.code(y.dtype), N, H, W, C, mean, rstd, scale, shift, sums, st)
         coef = self._coefficients(sums, N * H * W, mean, rstd)
         dy = e.empty(y.shape, y.dtype)
         lib.maxpool_bn_bwd_apply(d, d2, argmax, y, e.code(y.dtype), dy, N, H, W, C, coef, scale, shift, st)
@@ -376,7 +417,7 @@ class _Shortcut:
         self.bn = BatchNormRelu(vs, scope, filters_out, relu=False)
         self.in_shape = None
 
-    def __call__(self, x, training):
+    def _pre(self, x):
         if self.resnet_d:
             e = get_engine()
             N, H, W, C = x.shape
@@ -386,10 +427,23 @@ class _Shortcut:
             lib.avgpool2x2_fwd(x, y, e.code(x.dtype), N, H, W, C, s, stream_ptr())
             self.in_shape = (N, H, W, C)
             x = y
-        return conv_bn(self.conv, self.bn, x, training)
+        return x
+
+    def __call__(self, x, training):
+        return conv_bn(self.conv, self.bn, self._pre(x), training)
+
+    def forward_raw(self, x):
+        """Training only: the conv output and its batch statistics; the BatchNorm is applied by the block tail
+        (`BatchNormRelu.forward_tail2`)."""
+        e = get_engine()
+        sums = e.sums(2 * self.conv.cout)
+        return self.conv.op.forward(self._pre(x), True, bn_sums=sums), sums
 
     def backward(self, d):
-        d = self.conv.backward(self.bn.backward(d))
+        return self.backward_conv(self.bn.backward(d))
+
+    def backward_conv(self, d):
+        d = self.conv.backward(d)
         if self.resnet_d:
             e = get_engine()
             N, H, W, C = self.in_shape
@@ -570,23 +624,37 @@ class ResidualBlock:  # pylint: disable=missing-docstring
         self.cout = filters
 
     def __call__(self, inputs, training):
-        shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
+        self.fused_tail = (training and self.shortcut is not None and self.se_layer is None and
+                           BatchNormRelu.tail2_enabled())
+        if self.fused_tail:
+            ys, sums_s = self.shortcut.forward_raw(inputs)
+        else:
+            shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
         x = conv_bn(self.c1, self.b1, inputs, training)
         if self.se_layer is not None:
             x = self.se_layer(conv_bn(self.c2, self.b2, x, training), training)
             return self.add_relu(x, shortcut, training)
+        if self.fused_tail:
+            sums = get_engine().sums(2 * self.c2.cout)
+            return self.b2.forward_tail2(self.c2.op.forward(x, True, bn_sums=sums), sums, ys, self.shortcut.bn, sums_s)
         return conv_bn(self.c2, self.b2, x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :382
 
     def backward(self, d_out, d_out2=None):
+        dys = None
         if self.se_layer is not None:
             d_out = self.add_relu.backward(d_out, d_out2)
             dy = self.b2.backward(self.se_layer.backward(d_out))
+        elif self.fused_tail:
+            dy, dys = self.b2.backward_tail2(d_out, d_out2)
         else:
             dy = self.b2.backward(d_out, d_out2)      # d_out <- (d_out + d_out2) * [out > 0]
         d = self.c2.backward(dy)
         d = self.b1.backward(d)
         dx_a = self.c1.backward(d)
-        dx_b = d_out if self.shortcut is None else self.shortcut.backward(d_out)
+        if dys is not None:
+            dx_b = self.shortcut.backward_conv(dys)
+        else:
+            dx_b = d_out if self.shortcut is None else self.shortcut.backward(d_out)
         return dx_a, dx_b
 
 
@@ -612,18 +680,29 @@ class BottleneckBlock:
         self.cout = 4 * filters
 
     def __call__(self, inputs, training):
-        shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
+        self.fused_tail = (training and self.shortcut is not None and self.se_layer is None and
+                           BatchNormRelu.tail2_enabled())
+        if self.fused_tail:
+            ys, sums_s = self.shortcut.forward_raw(inputs)
+        else:
+            shortcut = inputs if self.shortcut is None else self.shortcut(inputs, training)
         x = conv_bn(self.c1, self.b1, inputs, training)
         x = self.sk(x, training) if self.sk is not None else conv_bn(self.c2, self.b2, x, training)
         if self.se_layer is not None:
             x = self.se_layer(conv_bn(self.c3, self.b3, x, training), training)
             return self.add_relu(x, shortcut, training)
+        if self.fused_tail:
+            sums = get_engine().sums(2 * self.c3.cout)
+            return self.b3.forward_tail2(self.c3.op.forward(x, True, bn_sums=sums), sums, ys, self.shortcut.bn, sums_s)
         return conv_bn(self.c3, self.b3, x, training, residual=shortcut, relu=True)     # relu(inputs + shortcut), :487
 
     def backward(self, d_out, d_out2=None):
+        dys = None
         if self.se_layer is not None:
             d_out = self.add_relu.backward(d_out, d_out2)
             dy = self.b3.backward(self.se_layer.backward(d_out))
+        elif self.fused_tail:
+            dy, dys = self.b3.backward_tail2(d_out, d_out2)
         else:
             dy = self.b3.backward(d_out, d_out2)
         d = self.c3.backward(dy)
@@ -634,7 +713,10 @@ class BottleneckBlock:
             d = self.c2.backward(d)
         d = self.b1.backward(d)
         dx_a = self.c1.backward(d)
-        dx_b = d_out if self.shortcut is None else self.shortcut.backward(d_out)
+        if dys is not None:
+            dx_b = self.shortcut.backward_conv(dys)
+        else:
+            dx_b = d_out if self.shortcut is None else self.shortcut.backward(d_out)
         return dx_a, dx_b
 
 

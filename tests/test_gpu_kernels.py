@@ -429,8 +429,8 @@ def test_preprocess_image_entry_point(eng):
     out = D.preprocess_image(im, 64, 64, is_training=True, color_jitter_strength=1.0, draws=d)
     ref = OD.preprocess_for_train(im.double() / 255.0, 64, 64, d)
     assert out.shape == (64, 64, 3) and (out.cpu().double() - ref).abs().max() < 2e-5
-    with pytest.raises(NotImplementedError):
-        D.preprocess_image(im, 64, 64, is_training=False)
+    ev = D.preprocess_image(im, 64, 64, is_training=False)              # central crop + bicubic resize + clip
+    assert (ev.cpu().double() - OD.preprocess_for_eval(im.double() / 255.0, 64, 64)).abs().max() < 2e-5
 
 
 def test_se_layer_fwd_bwd(eng, flags):
@@ -461,3 +461,113 @@ def test_se_layer_fwd_bwd(eng, flags):
     assert rel_err(dx, xo.grad) < 1e-5
     for v in vs.trainable:
         assert rel_err(v.grad, P[v.name].grad) < 1e-4, v.name
+
+
+# --------------------------------------------------------------------------
+# stem: BatchNorm + ReLU + MaxPooling2D fused (bf16 kernels) against the unfused kernel chain
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize('N,H,W,C,two', [(3, 16, 16, 64, True), (2, 10, 14, 64, False), (2, 9, 7, 128, True), (1, 112, 112, 64, True)])
+def test_fused_bn_relu_maxpool_bf16(eng, N, H, W, C, two):
+    """`simclr_bn_relu_maxpool_fwd` / `simclr_maxpool_bn_bwd_reduce` (pooled-domain reduction over ysel) /
+    `simclr_maxpool_bn_bwd_apply` == bn_apply(relu) -> maxpool3x3s2 -> maxpool bwd -> BatchNorm backward formulas."""
+    from simclr_b200._lib import lib, stream_ptr
+    torch.manual_seed(N * H + C)
+    bf = torch.bfloat16
+    st = stream_ptr()
+    y = (torch.randn(N, H, W, C) * 1.5 + 0.2).to(bf).cuda()
+    scale = (torch.randn(C) * 0.8).cuda(); shift = (torch.randn(C) * 0.3).cuda()      # both signs of scale
+    mean = torch.randn(C).cuda() * 0.1; rstd = (torch.rand(C) + 0.5).cuda()
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    # reference chain
+    z = torch.empty_like(y)
+    lib.bn_apply(y, 1, None, z, 1, N * H * W, C, scale, shift, 1, st)
+    p_ref = torch.empty(N, Ho, Wo, C, dtype=bf, device='cuda'); am_ref = torch.empty(N, Ho, Wo, C, dtype=torch.uint8, device='cuda')
+    lib.maxpool3x3s2_fwd(z, p_ref, am_ref, 1, N, H, W, C, st)
+    # fused forward
+    p = torch.empty_like(p_ref); am = torch.empty_like(am_ref); ysel = torch.empty_like(p_ref)
+    lib.bn_relu_maxpool_fwd(y, 1, scale, shift, p, am, ysel, N, H, W, C, st)
+    assert torch.equal(p, p_ref) and torch.equal(am, am_ref)
+    # ysel = y at the argmax tap (pad_before = 0 for these shapes' SAME padding when the total pad is 1, else 1)
+    pb_h = max((Ho - 1) * 2 + 3 - H, 0) // 2; pb_w = max((Wo - 1) * 2 + 3 - W, 0) // 2
+    code = am.long()
+    n_i = torch.arange(N, device='cuda').view(N, 1, 1, 1).expand_as(code)
+    h_i = torch.arange(Ho, device='cuda').view(1, Ho, 1, 1) * 2 - pb_h + code // 3
+    w_i = torch.arange(Wo, device='cuda').view(1, 1, Wo, 1) * 2 - pb_w + code % 3
+    c_i = torch.arange(C, device='cuda').view(1, 1, 1, C).expand_as(code)
+    assert torch.equal(ysel, y[n_i, h_i, w_i, c_i])
+    # backward reference: g = bf16(d + d2) routed by the unfused pooling backward, masked by z > 0
+    d = torch.randn(N, Ho, Wo, C).to(bf).cuda()
+    d2 = torch.randn(N, Ho, Wo, C).to(bf).cuda() if two else None
+    g = (d.float() + d2.float()).to(bf) if two else d
+    dz = torch.empty_like(y)
+    lib.maxpool3x3s2_bwd(g, am_ref, dz, 1, N, H, W, C, st)
+    dzm = torch.where(z.float() > 0, dz.float(), torch.zeros((), device='cuda')).double()
+    yd = y.double()
+    s0 = dzm.sum(dim=(0, 1, 2)); s1 = (dzm * (yd - mean.double())).sum(dim=(0, 1, 2)) * rstd.double()
+    sums = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+    lib.maxpool_bn_bwd_reduce(d, d2, am, y, ysel, 1, N, H, W, C, mean, rstd, scale, shift, sums, st)
+    ref = torch.cat([s0, s1])
+    # pooled-domain sums differ from per-pixel ones only by the bf16 rounding of multi-window gradient sums
+    assert (sums - ref).abs().max() < 2e-3 * ref.abs().max() + 1e-2, ((sums - ref).abs().max(), ref.abs().max())
+    sums_px = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+    lib.maxpool_bn_bwd_reduce(d, d2, am, y, None, 1, N, H, W, C, mean, rstd, scale, shift, sums_px, st)   # per-pixel kernel
+    assert (sums_px - ref).abs().max() < 1e-4 * ref.abs().max() + 1e-4
+    coef = (torch.randn(3, C) * 0.5).cuda().contiguous()
+    dy = torch.empty_like(y)
+    lib.maxpool_bn_bwd_apply(d, d2, am, y, 1, dy, N, H, W, C, coef, scale, shift, st)
+    k1, k2, k3 = coef[0].double(), coef[1].double(), coef[2].double()
+    dy_ref = k1 * dzm + k2 * yd + k3
+    err = (dy.double() - dy_ref).abs()
+    assert (err <= dy_ref.abs() * 2.0 ** -8 + 1e-6).all(), err.max()      # half a bf16 ulp of the exact value
+
+
+def test_global_avgpool_bwd_bf16(eng):
+    from simclr_b200._lib import lib, stream_ptr
+    torch.manual_seed(6)
+    for dy_dt, code in ((torch.float32, 0), (torch.bfloat16, 1)):
+        dy = torch.randn(5, 256).to(dy_dt).cuda()
+        dx = torch.empty(5, 7, 7, 256, dtype=torch.bfloat16, device='cuda')
+        lib.global_avgpool_bwd(dy, code, dx, 1, 5, 49, 256, stream_ptr())
+        ref = (dy.float() * (1.0 / 49.0)).to(torch.bfloat16).view(5, 1, 1, 256).expand(5, 7, 7, 256)
+        assert torch.equal(dx, ref)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('rows,C,two', [(1000, 256, True), (37, 64, False), (3 * 28 * 28, 512, True), (50, 2048, True)])
+def test_projection_tail_dual_batchnorm(eng, dtype, rows, C, two):
+    """simclr_bn_apply2_relu_mask / simclr_bn_bwd_reduce2_bits / simclr_bn_bwd_apply2_coef == the two-BatchNorm chain
+    (shortcut BN applied and stored, then the block tail) they replace: bit-identical outputs, sums to fp64 noise."""
+    from simclr_b200._lib import lib, stream_ptr, DTYPE_CODE
+    torch.manual_seed(rows + C)
+    st = stream_ptr()
+    code = DTYPE_CODE[dtype]
+    y = torch.randn(rows, C).to(dtype).cuda(); y2 = (torch.randn(rows, C) * 0.7 + 0.1).to(dtype).cuda()
+    par = lambda s=1.0: (torch.randn(C) * s).cuda()
+    scale, shift, scale2, shift2 = par(0.8), par(0.3), par(0.6), par(0.2)
+    mean, mean2 = par(0.1), par(0.1); rstd, rstd2 = (torch.rand(C) + 0.5).cuda(), (torch.rand(C) + 0.5).cuda()
+    # forward reference
+    zs = torch.empty_like(y2); z_ref = torch.empty_like(y); bits_ref = torch.empty(rows * C // 8, dtype=torch.uint8, device='cuda')
+    lib.bn_apply(y2, code, None, zs, code, rows, C, scale2, shift2, 0, st)
+    lib.bn_apply_relu_mask(y, code, zs, z_ref, code, rows, C, scale, shift, bits_ref, st)
+    z = torch.empty_like(y); bits = torch.empty_like(bits_ref)
+    lib.bn_apply2_relu_mask(y, y2, code, z, code, rows, C, scale, shift, scale2, shift2, bits, st)
+    assert torch.equal(z, z_ref) and torch.equal(bits, bits_ref)
+    # backward reduce
+    a = torch.randn(rows, C).to(dtype).cuda(); a2 = torch.randn(rows, C).to(dtype).cuda() if two else None
+    a_ref = a.clone(); a_f = a.clone()
+    s_ref = torch.zeros(2 * C, dtype=torch.float64, device='cuda'); s2_ref = torch.zeros_like(s_ref)
+    lib.bn_bwd_reduce_bits(a_ref, a2, bits, code, y, code, rows, C, mean, rstd, s_ref, st)
+    lib.bn_bwd_reduce(a_ref, None, None, code, y2, code, rows, C, mean2, rstd2, s2_ref, st)
+    s = torch.zeros_like(s_ref); s2 = torch.zeros_like(s_ref)
+    lib.bn_bwd_reduce2_bits(a_f, a2, bits, code, y, y2, code, rows, C, mean, rstd, mean2, rstd2, s, s2, st)
+    assert torch.equal(a_f, a_ref)
+    for got, want in ((s, s_ref), (s2, s2_ref)):
+        assert (got - want).abs().max() <= 1e-6 * want.abs().max() + 1e-9, (got - want).abs().max()
+    # backward apply
+    coef, coef2 = (torch.randn(3, C) * 0.5).cuda().contiguous(), (torch.randn(3, C) * 0.5).cuda().contiguous()
+    dy_ref, dy2_ref = torch.empty_like(y), torch.empty_like(y)
+    lib.bn_bwd_apply_coef(a_ref, code, y, code, dy_ref, code, rows, C, coef, None, None, st)
+    lib.bn_bwd_apply_coef(a_ref, code, y2, code, dy2_ref, code, rows, C, coef2, None, None, st)
+    dy, dy2 = torch.empty_like(y), torch.empty_like(y)
+    lib.bn_bwd_apply2_coef(a_f, code, y, y2, code, dy, dy2, code, rows, C, coef, coef2, st)
+    assert torch.equal(dy, dy_ref) and torch.equal(dy2, dy2_ref)

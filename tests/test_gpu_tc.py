@@ -237,3 +237,31 @@ def test_tc_dgrad_bf16_out(case):
     lib.conv2d_dgrad_tc(dy.cuda(), wd, dx, 1, 1, N, H, W, Cin, Cout, k, k, s, stream_ptr())
     torch.cuda.synchronize()
     assert rel_err(dx, xo.grad) < 8e-3
+
+
+def test_pack_weights_multi_matches_single():
+    """One-launch packing of many layers (balanced 32x32 transposition tiles) == per-layer `simclr_pack_conv_weight`,
+    including the stem layout (Cs = 4), Kp padding, Cout not a multiple of 32 and layers without a dgrad operand."""
+    from simclr_b200._lib import lib, stream_ptr
+    torch.manual_seed(0)
+    st = stream_ptr()
+    layers = [(7, 3, 4, 64, False), (1, 64, 64, 256, True), (3, 64, 64, 64, True), (3, 128, 128, 128, True),
+              (1, 2048, 2048, 16, True), (1, 512, 512, 1000, False), (3, 8, 8, 24, True), (1, 256, 256, 40, True)]
+    rows, keep = [], []
+    for k, Cin, Cs, Cout, has_wd in layers:
+        w = torch.randn(k, k, Cin, Cout, device='cuda')
+        Kp = ((k * (k + 1) if Cs == 4 else k * k) * Cs + 63) // 64 * 64
+        Kdp = (k * k * Cout + 63) // 64 * 64
+        wf = torch.full((Cout, Kp), 7.0, dtype=torch.bfloat16, device='cuda'); wf_ref = torch.empty_like(wf)
+        wd = torch.full((Cin, Kdp), 7.0, dtype=torch.bfloat16, device='cuda') if has_wd else None
+        wd_ref = torch.empty_like(wd) if has_wd else None
+        lib.pack_conv_weight(w, wf_ref, wd_ref, 1, k, k, Cin, Cs, Cout, Kp, st)
+        rows.append([w.data_ptr(), wf.data_ptr(), wd.data_ptr() if has_wd else 0, k, k, Cin, Cs, Cout, Kp, Kdp if has_wd else 0])
+        keep.append((w, wf, wf_ref, wd, wd_ref))
+    table = torch.tensor(rows, dtype=torch.int64).cuda()
+    lib.pack_conv_weights_multi(table, len(rows), st)
+    torch.cuda.synchronize()
+    for i, (w, wf, wf_ref, wd, wd_ref) in enumerate(keep):
+        assert torch.equal(wf, wf_ref), 'wf of layer %d' % i
+        if wd is not None:
+            assert torch.equal(wd, wd_ref), 'wd of layer %d' % i
