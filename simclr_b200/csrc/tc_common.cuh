@@ -338,6 +338,11 @@ inline int make_tmap_im2col(CUtensorMap* map, const void* base, int elt_bytes, u
   return SIMCLR_OK;
 }
 
+// 7x7 stride-2 stem fprop from a slab of 16-byte pixel pairs, no im2col copy (tc_stem.cu)
+bool stem7x7_applicable(int dtype, int out_dtype, int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t n_out, int64_t R,
+                        int64_t S, int64_t stride, int64_t P, int64_t Q, const void* src, const void* wk, const void* out);
+int run_stem7x7(const void* src, const void* wk, void* out, int64_t N, int64_t H, int64_t W, int64_t n_out, cudaStream_t st,
+                double* bn_sums);
 // 3x3 stride-1 fprop / dgrad with halo reuse (tc_halo.cu); see run_halo3x3 for the argument meaning
 bool halo3x3_applicable(int dtype, int out_dtype, int64_t N, int64_t H, int64_t W, int64_t C, int64_t n_out, int64_t R,
                         int64_t S, int64_t stride, const void* src, const void* wk, const void* out);

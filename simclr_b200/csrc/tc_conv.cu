@@ -989,6 +989,9 @@ int run_igemm(int mode, const void* src, const void* wk, void* out, int dtype, i
   if (!aligned16(src) || !aligned16(wk)) { set_error("%s: operands must be 16-byte aligned", what); return SIMCLR_ERR_INVALID_ARG; }
   const int64_t M = N * P * Q;
   if (M >= (1ll << 31)) { set_error("%s: M too large", what); return SIMCLR_ERR_UNSUPPORTED; }
+  // stem: slab of pixel pairs read through overlapping no-swizzle descriptors (tc_stem.cu)
+  if (mode == 0 && smallc && !accum && stem7x7_applicable(dtype, out_dtype, N, Hs, Ws, Cs, n_out, R, S, stride, P, Q, src, wk, out))
+    return run_stem7x7(src, wk, out, N, Hs, Ws, n_out, st, bn_sums);
   // 64 / 128-channel 3x3 stride-1 layers: halo-reuse kernel (one slab load instead of nine im2col loads)
   if (!accum && P == Hs && Q == Ws && halo3x3_applicable(dtype, out_dtype, N, Hs, Ws, Cs, n_out, R, S, stride, src, wk, out))
     return run_halo3x3(mode, src, wk, out, N, Hs, Ws, Cs, n_out, st, bn_sums);

@@ -507,8 +507,12 @@ def test_fused_bn_relu_maxpool_bf16(eng, N, H, W, C, two):
     sums = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
     lib.maxpool_bn_bwd_reduce(d, d2, am, y, ysel, 1, N, H, W, C, mean, rstd, scale, shift, sums, st)
     ref = torch.cat([s0, s1])
-    # pooled-domain sums differ from per-pixel ones only by the bf16 rounding of multi-window gradient sums
-    assert (sums - ref).abs().max() < 2e-3 * ref.abs().max() + 1e-2, ((sums - ref).abs().max(), ref.abs().max())
+    # the same sums taken over the pooled tensor (every window routes its gradient to one pixel): what the kernel computes
+    gm = torch.where(p_ref.float() > 0, g.float(), torch.zeros((), device='cuda')).double()
+    ref_pooled = torch.cat([gm.sum(dim=(0, 1, 2)), (gm * (ysel.double() - mean.double())).sum(dim=(0, 1, 2)) * rstd.double()])
+    assert (sums - ref_pooled).abs().max() < 1e-5 * ref_pooled.abs().max() + 1e-6, (sums - ref_pooled).abs().max()
+    # ... and they differ from the per-pixel sums only by the bf16 rounding of multi-window gradient sums
+    assert (sums - ref).norm() < 0.02 * ref.norm(), ((sums - ref).norm(), ref.norm())
     sums_px = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
     lib.maxpool_bn_bwd_reduce(d, d2, am, y, None, 1, N, H, W, C, mean, rstd, scale, shift, sums_px, st)   # per-pixel kernel
     assert (sums_px - ref).abs().max() < 1e-4 * ref.abs().max() + 1e-4

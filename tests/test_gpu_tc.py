@@ -41,6 +41,11 @@ CASES = [
     (2, 27, 28, 128, 128, 128, 3, 1),    # H not a multiple of the rows per tile: last tile clipped by the TMA store
     (5, 18, 30, 64, 64, 64, 3, 1),       # Wp 32, more tiles than one wave of a small grid
     (1, 10, 62, 64, 64, 64, 3, 1),       # widest supported row (Wp 64)
+    # stem kernel (tc_stem.cu): slab of pixel pairs, overlapping no-swizzle descriptors, one output row per tile
+    (2, 224, 224, 3, 4, 64, 7, 2),       # the benchmark shape: Q = 112 of 128 GEMM rows real
+    (40, 16, 16, 3, 4, 64, 7, 2),        # 320 tiles: several per CTA, slab ring and both accumulators wrap
+    (2, 64, 64, 3, 4, 128, 7, 2),        # width multiplier 2: two 64-column boxes per tile
+    (1, 48, 40, 3, 4, 256, 7, 2),        # width multiplier 4, rectangular
 ]
 
 
