@@ -343,6 +343,10 @@ bool stem7x7_applicable(int dtype, int out_dtype, int64_t N, int64_t H, int64_t 
                         int64_t S, int64_t stride, int64_t P, int64_t Q, const void* src, const void* wk, const void* out);
 int run_stem7x7(const void* src, const void* wk, void* out, int64_t N, int64_t H, int64_t W, int64_t n_out, cudaStream_t st,
                 double* bn_sums);
+bool stem7x7_wgrad_applicable(int dtype, int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cin, int64_t Cout, int64_t R,
+                              int64_t S, int64_t stride, const void* x, const void* dy, const void* dw);
+int run_stem7x7_wgrad(const void* x, const void* dy, float* dw, int64_t N, int64_t H, int64_t W, int64_t Cin, cudaStream_t st,
+                      bool zero);
 // 3x3 stride-1 fprop / dgrad with halo reuse (tc_halo.cu); see run_halo3x3 for the argument meaning
 bool halo3x3_applicable(int dtype, int out_dtype, int64_t N, int64_t H, int64_t W, int64_t C, int64_t n_out, int64_t R,
                         int64_t S, int64_t stride, const void* src, const void* wk, const void* out);

@@ -1228,6 +1228,8 @@ static int wgrad_tc_impl(const void* x, const void* dy, float* dw, int dtype, in
   }
   if (halo3x3_wgrad_applicable(dtype, N, H, W, Cs, Cin, Cout, R, S, stride, x, dy, dw))
     return run_halo3x3_wgrad(x, dy, dw, N, H, W, st, zero);
+  if (stem7x7_wgrad_applicable(dtype, N, H, W, Cs, Cin, Cout, R, S, stride, x, dy, dw))
+    return run_stem7x7_wgrad(x, dy, dw, N, H, W, Cin, st, zero);
   const int es = dtype == SIMCLR_BF16 ? 2 : 4;
   const int ATOM_E = 128 / es, CH = 16 / es;
   bool smallc = (dtype == SIMCLR_BF16 && Cs == 4);

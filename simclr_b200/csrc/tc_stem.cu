@@ -247,6 +247,134 @@ stem7x7_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, CFG::TMEM_COLS); }
 }
 
+// ===========================================================================
+// wgrad of the stem from the same slab:  dW[(r, slot, c)][co] = sum over pixels  X[slab row r, pair q + slot/2][..] * dY[q][co]
+// computed transposed, D_r[co][k'] (k' = slot*4 + c, 32 per filter row) = sum_q dY[q][co] * slab_r[q][k']:
+//   A = dY tile [pixels][64 co]   MN-major, 128B-swizzled (M = 64 output channels, K = pixels), TMA box of Q rows
+//   B = slab row r                MN-major, NOT swizzled: 8 k' (16 B) x 8 pixels (16 B apart) core matrices; the next
+//                                 8 k' sit ONE pair further (16 B, overlapping), the next 8 pixels 128 B further
+// Seven accumulators [64 x 32] (one per filter row) live in TMEM for the whole kernel; every CTA sweeps its output
+// rows and adds its partial into dW [7][7][Cin][64] with fp32 atomics (9408 per CTA).  Operand buffers are zeroed
+// once: dY rows beyond Q stay zero (the TMA box never writes them), so padded pixels contribute nothing.
+// ===========================================================================
+constexpr int SWG_STAGES = 3;
+struct StemWGeom {
+  int P, Q, N, num_tiles;
+  int box_pairs, box_bytes;      // slab box
+  int ksteps;                    // ceil(Q / 16) MMAs (K = 16 pixels) per filter row
+  int dy_bytes, stage_bytes;     // dY part (ksteps * 2048) and whole stage (1024-byte multiple)
+  int Cin;
+  int variant;                   // bit 0: swap LBO / SBO of the slab descriptor; bit 1: TMEM rows in lanes 0-63 (bring-up switches)
+};
+
+__global__ void __launch_bounds__(192, 1)
+stem7x7_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                     const StemWGeom g, float* __restrict__ dw) {
+  constexpr uint32_t IDESC = make_idesc(false, 64, 32, true, true);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)SWG_STAGES * g.stage_bytes);
+  uint64_t* full = bars;                      // [SWG_STAGES]
+  uint64_t* empty = bars + SWG_STAGES;        // [SWG_STAGES]
+  uint64_t* acc_full = empty + SWG_STAGES;    // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < SWG_STAGES * g.stage_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SWG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_dy); }
+  if (warp == 4) tmem_alloc(tmem_ptr, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const bool has_work = (int)blockIdx.x < g.num_tiles;
+
+  if (warp < 4) {
+    // ------------------------------ epilogue (once) ------------------------------
+    if (has_work) {
+      mbar_wait(acc_full, 0, 310);
+      tc_fence_after();
+      // M = 64 accumulator rows in TMEM: 16 rows per 32-lane sub-partition (lanes 0-15), or lanes 0-63
+      const bool lanes64 = (g.variant & 2) != 0;
+      const int co = lanes64 ? warp * 32 + lane : warp * 16 + lane;
+      const bool act = lanes64 ? warp < 2 : lane < 16;
+#pragma unroll 1
+      for (int r = 0; r < 7; ++r) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + r * 32, acc);
+        tmem_ld_wait();
+        if (act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int sp = j >> 2, c = j & 3;                 // column slot (0: the zero slot), stored channel
+            if (sp >= 1 && c < g.Cin) atomicAdd(dw + ((size_t)((r * 7 + sp - 1) * g.Cin + c)) * 64 + co, __uint_as_float(acc[j]));
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------ MMA issuer ----------------------------
+    constexpr uint32_t HI_A = desc_hi_sw128(1024);
+    const bool swap = (g.variant & 1) != 0;
+    // slab operand, no swizzle: stride between 8-k' core matrices 16 B, between 8-pixel groups 128 B
+    const uint32_t hi_b = uniform_u32((swap ? 8u : 1u) | (1u << 14));          // SBO field
+    const uint32_t lbo_b = uniform_u32((swap ? 1u : 8u) << 16);                 // LBO field
+    int ss = 0; uint32_t sphase = 0;
+    const uint32_t smem_lo = uniform_u32((smem_u32(smem) & 0x3FFFFu) >> 4);
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), dy16 = (uint32_t)(g.dy_bytes >> 4), pitch16 = (uint32_t)g.box_pairs;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&full[ss], sphase, 320);
+      tc_fence_after();
+      const uint32_t dy_lo = (smem_lo + (uint32_t)ss * stage16) | (1u << 16);
+      const uint32_t x_lo = (smem_lo + (uint32_t)ss * stage16 + dy16) | lbo_b;
+      if (elect_one()) {
+        // K step outermost: consecutive MMAs go to seven DIFFERENT accumulators (no back-to-back dependence on one)
+#pragma unroll 1
+        for (int ks = 0; ks < g.ksteps; ++ks) {       // 16 pixels per MMA: 16 dY rows of 128 B, 16 pairs of the slab row
+          const uint64_t ad = desc_pack(dy_lo + ks * 128, HI_A);
+#pragma unroll
+          for (int r = 0; r < 7; ++r)
+            umma<false>(tmem_u + r * 32, ad, desc_pack(x_lo + r * pitch16 + ks * 16, hi_b), IDESC, (!first || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[ss]);
+      }
+      __syncwarp();
+      first = false;
+      if (++ss == SWG_STAGES) { ss = 0; sphase ^= 1; }
+    }
+    if (has_work && elect_one()) umma_commit(acc_full);
+    __syncwarp();
+  } else {
+    // ------------------------------ TMA producer --------------------------
+    if (lane == 0) {
+      int ss = 0; uint32_t sphase = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const int n = tile / g.P, p = tile - n * g.P;
+        mbar_wait(&empty[ss], sphase ^ 1, 330);
+        uint8_t* st = smem + (size_t)ss * g.stage_bytes;
+        mbar_arrive_expect_tx(&full[ss], g.box_bytes + g.Q * 128);
+        tma_load_2d(st, &tmap_dy, &full[ss], 0, tile * g.Q);
+        st_tma_load_4d(st + g.dy_bytes, &tmap_x, &full[ss], 0, -2, 2 * p - 3, n);
+        if (++ss == SWG_STAGES) { ss = 0; sphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
 // x [N][H][W][4] bf16 seen as [N][H][W/2][8]: 16-byte pixel pairs, no swizzle
 int make_tmap_pairs(CUtensorMap* map, const void* base, uint64_t N, uint64_t H, uint64_t W2, uint32_t box_pairs, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_tiled();
@@ -324,6 +452,52 @@ int run_stem7x7(const void* src, const void* wk, void* out, int64_t N, int64_t H
   if (n_out == 128) return STEM(128);
   return STEM(256);
 #undef STEM
+}
+
+bool stem7x7_wgrad_applicable(int dtype, int64_t N, int64_t H, int64_t W, int64_t Cs, int64_t Cin, int64_t Cout, int64_t R,
+                              int64_t S, int64_t stride, const void* x, const void* dy, const void* dw) {
+  const char* e = getenv("SIMCLR_TC_STEM_WGRAD");
+  if (e && e[0] == '0') return false;
+  if (dtype != SIMCLR_BF16 || Cs != 4 || Cin > 4 || Cout != 64 || R != 7 || S != 7 || stride != 2) return false;
+  if (W % 2 || H % 2) return false;
+  const int64_t Q = W / 2;
+  if (Q < 8 || Q > 128) return false;
+  if (N * (H / 2) >= (1ll << 31) / 128) return false;
+  if (!aligned16(x) || !aligned16(dy) || !aligned16(dw)) return false;
+  return get_encode_tiled() != nullptr;
+}
+
+// x [N][H][W][4] bf16, dy [N][H/2][W/2][64] bf16, dw [7][7][Cin][64] fp32 (+=)
+int run_stem7x7_wgrad(const void* x, const void* dy, float* dw, int64_t N, int64_t H, int64_t W, int64_t Cin, cudaStream_t st,
+                      bool zero) {
+  StemWGeom g;
+  g.P = (int)(H / 2); g.Q = (int)(W / 2); g.N = (int)N; g.num_tiles = (int)(N * g.P);
+  g.box_pairs = g.Q + 3; g.box_bytes = 7 * g.box_pairs * 16;
+  g.ksteps = (g.Q + 15) / 16;
+  g.dy_bytes = g.ksteps * 2048;
+  // slab part: 7 rows + the pairs the last K step of the last filter row reaches beyond them
+  const int slab = 6 * g.box_pairs * 16 + (g.ksteps * 16 + 3) * 16 + 16;
+  const int slab_b = slab > 7 * g.box_pairs * 16 ? slab : 7 * g.box_pairs * 16;
+  g.stage_bytes = (g.dy_bytes + slab_b + 1023) / 1024 * 1024;
+  g.Cin = (int)Cin;
+  const char* v = getenv("SIMCLR_STEM_WG_VARIANT");
+  g.variant = v ? atoi(v) : 0;
+  CUtensorMap tx, tdy;
+  int rc = make_tmap_pairs(&tx, x, (uint64_t)N, (uint64_t)H, (uint64_t)(W / 2), (uint32_t)g.box_pairs, 7);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tdy, dy, 2, (uint64_t)(N * g.P * g.Q), 64, 128, (uint32_t)g.Q, 64);
+  if (rc) return rc;
+  if (zero && !accumulate_prezeroed()) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)(49 * Cin * 64) * sizeof(float), st);
+    if (e != cudaSuccess) { set_error("stem7x7_wgrad: memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  const size_t smem = 1024 + (size_t)SWG_STAGES * g.stage_bytes + 256;
+  cudaError_t e = cudaFuncSetAttribute(stem7x7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("stem7x7_wgrad: cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return (int)e; }
+  const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
+  stem7x7_wgrad_kernel<<<grid, 192, smem, st>>>(tx, tdy, g, dw);
+  SIMCLR_CHECK_LAUNCH();
+  return SIMCLR_OK;
 }
 
 }  // namespace tc
