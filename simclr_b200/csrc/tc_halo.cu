@@ -384,16 +384,22 @@ halo3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const uint32_t x_lo = smem_lo + (uint32_t)ss * (WG_STAGE_BYTES >> 4);
       const uint32_t dy_lo = x_lo + (SLAB_BYTES >> 4);
       if (elect_one()) {
+        // K step outermost, the five accumulators innermost: consecutive MMAs never accumulate into the same columns
+        // (for the stem's small M64 x N32 MMAs that order was worth 1.29 -> 0.72 ms; here 0.81 -> 0.76 ms)
+        uint32_t a_lo[5];
 #pragma unroll
         for (int pr = 0; pr < 5; ++pr) {
           const int ta = 2 * pr, tb = pr == 4 ? 8 : 2 * pr + 1;
           const int offa = (ta / 3) * Wp + ta % 3, offb = (tb / 3) * Wp + tb % 3;
-          const uint32_t a_lo = (x_lo + (uint32_t)offa * 8u) | ((((uint32_t)(offb - offa) * 8u) & 0x3FFFu) << 16);   // LBO = (offb - offa) * 128 B
-          const uint32_t b_lo = dy_lo | (1u << 16);
+          a_lo[pr] = (x_lo + (uint32_t)offa * 8u) | ((((uint32_t)(offb - offa) * 8u) & 0x3FFFu) << 16);   // LBO = (offb - offa) * 128 B
+        }
+        const uint32_t b_lo = dy_lo | (1u << 16);
 #pragma unroll
-          for (int k = 0; k < 8; ++k)        // 16 pixels (16 rows of 128 B) per MMA
-            umma<false>(tmem_u + pr * 64, desc_pack(a_lo + k * 128, HI), desc_pack(b_lo + k * 128, HI), IDESC,
-                        (!first || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k) {        // 16 pixels (16 rows of 128 B) per MMA
+          const uint64_t bd = desc_pack(b_lo + k * 128, HI);
+#pragma unroll
+          for (int pr = 0; pr < 5; ++pr)
+            umma<false>(tmem_u + pr * 64, desc_pack(a_lo[pr] + k * 128, HI), bd, IDESC, (!first || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty[ss]);
       }
