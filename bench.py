@@ -364,7 +364,7 @@ def run_b200(args):
                 traffic = None
         key = (args.resnet_depth, args.width_multiplier, S, args.sk_ratio > 0)
         step_tflops = (ips / world) * GFLOP_PER_IMAGE[key] / 1e3 if key in GFLOP_PER_IMAGE else None
-        roof = {'bound': 'tensor', 'kernel': 'igemm / wgrad / halo3x3 kernels (tcgen05 implicit GEMM, %d conv calls per step)' % sum(v[2] for v in by.values()),
+        roof = {'bound': 'tensor', 'kernel': 'igemm / wgrad / halo3x3 / stem7x7 kernels (tcgen05 implicit GEMM, %d conv calls per step)' % sum(v[2] for v in by.values()),
                 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops'],
                 'traffic': traffic, 'traffic_source': traffic_src, 'algorithmic_bytes': alg / n_launch,
                 'peak_source': peaks['which'],

@@ -18,6 +18,8 @@ cap r2_full_halo_wgrad halo3x3_wgrad 3 wgrad
 cap r2_full_igemm_3x3 igemm_kernel 16 fprop
 cap r2_full_igemm_1x1 igemm_kernel 1 fprop
 cap r2_full_wgrad wgrad_kernel 16 wgrad
+cap r2_full_stem_fprop stem7x7_kernel 0 fprop
+cap r2_full_stem_wgrad stem7x7_wgrad 0 wgrad
 timeout 200 ncu --set full --clock-control none -k "regex:bn_apply_kernel|bn_reduce_kernel|bn_bwd_apply_kernel" -c 3 -o gpurun_out/r2_full_bn \
   python scripts/bn_bench.py > gpurun_out/r2_full_bn.log 2>&1
 echo "ncu bn exit $?"

@@ -39,11 +39,11 @@ with open(out_txt, 'w') as fh:
         t = d['gpu__time_duration.sum']
         gb = (d.get('dram__bytes_read.sum', 0.0) + d.get('dram__bytes_write.sum', 0.0)) / 1e9
         fh.write('%-44s launches=%4d %10.3f ms %6.1f%%   dram %8.2f GB\n' % (k[:44], len(launches[k]), t, 100 * t / tot, gb))
-conv = [k for k in per if k.startswith(('igemm_kernel', 'wgrad_kernel', 'halo3x3_kernel', 'halo3x3_wgrad_kernel'))]
+conv = [k for k in per if k.startswith(('igemm_kernel', 'wgrad_kernel', 'halo3x3_kernel', 'halo3x3_wgrad_kernel', 'stem7x7_kernel', 'stem7x7_wgrad_kernel'))]
 cl = sum(len(launches[k]) for k in conv)
 cb = sum(per[k].get('dram__bytes_read.sum', 0.0) + per[k].get('dram__bytes_write.sum', 0.0) for k in conv)
 ct = sum(per[k]['gpu__time_duration.sum'] for k in conv)
-json.dump({'kernel': 'igemm_kernel/wgrad_kernel/halo3x3_kernel/halo3x3_wgrad_kernel', 'launches': cl, 'dram_bytes_per_launch': cb / max(cl, 1),
+json.dump({'kernel': 'igemm_kernel/wgrad_kernel/halo3x3_kernel/halo3x3_wgrad_kernel/stem7x7_kernel/stem7x7_wgrad_kernel', 'launches': cl, 'dram_bytes_per_launch': cb / max(cl, 1),
            'dram_bytes_per_step': cb, 'share_of_step_kernel_time': ct / tot,
            'workload': 'ResNet-50 1x, batch 512, 224x224, bf16', 'source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum'},
           open(out_json, 'w'), indent=1)

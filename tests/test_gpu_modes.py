@@ -111,9 +111,12 @@ def test_finetune_step_parity(flags, optimizer, ft_block, selector):
         Pn, _ = OL.lars_apply(Pt, Gt, Z, lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay,
                               exclude_from_weight_decay=OL.LARS_EXCLUDE)
     for v in trainer.model.trainable_variables:
-        upd, upd_ref = (v.value.double().cpu() - Pt[v.name]), Pn[v.name] - Pt[v.name]
+        # new weights against the rule's: 1e-4 of the update, plus the fp32 rounding of the stored weight itself
+        # (a small-learning-rate update is ~1e-5 of the weight: half an fp32 ulp of w is ~1e-3 of it)
+        upd_ref = Pn[v.name] - Pt[v.name]
         if upd_ref.norm() > 0:
-            assert rel_err(upd, upd_ref) < 1e-4, (v.name, rel_err(upd, upd_ref))
+            err = (v.value.double().cpu() - Pn[v.name]).norm()
+            assert err < 1e-4 * upd_ref.norm() + 2.0 ** -24 * Pt[v.name].norm(), (v.name, float(err), float(upd_ref.norm()))
     for v in trainer.model.variables:
         if v.name in frozen or (ft_block >= 0 and v.name in S_ and v.name in frozen):
             assert torch.equal(v.value, before[v.name]), 'frozen variable %s changed' % v.name
@@ -188,13 +191,14 @@ def test_preprocess_for_eval_and_input_pipeline(flags):
     same = DU.preprocess_image(images[2], 64, 64, is_training=False, test_crop=False)      # CIFAR-style: no crop
     assert (same.cpu() - images[2].float() / 255.0).abs().max() < 1e-6
     # pipeline: two views per sample for pretraining, one centre crop for eval
-    flags_def.set_flags(image_size=32, train_mode='pretrain', train_split='train', eval_split='validation')
+    # image_size > 32: the eval path centre-crops (tf2/data.py:87-92 switches test_crop off for CIFAR-sized inputs)
+    flags_def.set_flags(image_size=40, train_mode='pretrain', train_split='train', eval_split='validation')
     arr = np.random.RandomState(0).randint(0, 256, (40, 48, 56, 3), dtype=np.uint8)
     b = D.ArrayBuilder({'train': (arr, np.arange(40) % 10), 'validation': (arr[:10], np.arange(10) % 10)}, 10)
     it = D.build_input_fn(b, 16, None, True)(D.InputContext(1, 0, 1), seed=3)
     f, lab = next(it)
-    assert f.shape == (16, 32, 32, 6) and f.dtype == torch.float32 and f.is_cuda and lab.shape == (16, 10)
+    assert f.shape == (16, 40, 40, 6) and f.dtype == torch.float32 and f.is_cuda and lab.shape == (16, 10)
     assert float(f.min()) >= 0.0 and float(f.max()) <= 1.0 and not torch.equal(f[..., :3], f[..., 3:])
     assert torch.equal(lab.sum(1), torch.ones(16, device='cuda'))
     fe, le = next(D.build_input_fn(b, 8, None, False)(D.InputContext(1, 0, 1)))
-    assert fe.shape == (8, 32, 32, 3) and torch.equal(le.argmax(1).cpu(), torch.arange(8) % 10)
+    assert fe.shape == (8, 40, 40, 3) and torch.equal(le.argmax(1).cpu(), torch.arange(8) % 10)
