@@ -264,7 +264,6 @@ struct StemWGeom {
   int ksteps;                    // ceil(Q / 16) MMAs (K = 16 pixels) per filter row
   int dy_bytes, stage_bytes;     // dY part (ksteps * 2048) and whole stage (1024-byte multiple)
   int Cin;
-  int variant;                   // bit 0: swap LBO / SBO of the slab descriptor; bit 1: TMEM rows in lanes 0-63 (bring-up switches)
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -301,10 +300,9 @@ stem7x7_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     if (has_work) {
       mbar_wait(acc_full, 0, 310);
       tc_fence_after();
-      // M = 64 accumulator rows in TMEM: 16 rows per 32-lane sub-partition (lanes 0-15), or lanes 0-63
-      const bool lanes64 = (g.variant & 2) != 0;
-      const int co = lanes64 ? warp * 32 + lane : warp * 16 + lane;
-      const bool act = lanes64 ? warp < 2 : lane < 16;
+      // an M = 64 accumulator keeps 16 rows per 32-lane TMEM sub-partition (lanes 0-15 of each warp's quarter)
+      const int co = warp * 16 + lane;
+      const bool act = lane < 16;
 #pragma unroll 1
       for (int r = 0; r < 7; ++r) {
         uint32_t acc[32];
@@ -322,10 +320,10 @@ stem7x7_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   } else if (warp == 4) {
     // ------------------------------ MMA issuer ----------------------------
     constexpr uint32_t HI_A = desc_hi_sw128(1024);
-    const bool swap = (g.variant & 1) != 0;
-    // slab operand, no swizzle: stride between 8-k' core matrices 16 B, between 8-pixel groups 128 B
-    const uint32_t hi_b = uniform_u32((swap ? 8u : 1u) | (1u << 14));          // SBO field
-    const uint32_t lbo_b = uniform_u32((swap ? 1u : 8u) << 16);                 // LBO field
+    // slab operand, MN-major without swizzle: SBO = stride between 8-k' core matrices (16 B, overlapping),
+    // LBO = stride between 8-pixel groups (128 B) -- the roles are the reverse of the swizzled MN-major layouts
+    const uint32_t hi_b = uniform_u32(1u | (1u << 14));          // SBO field (16-byte units)
+    const uint32_t lbo_b = uniform_u32(8u << 16);                // LBO field
     int ss = 0; uint32_t sphase = 0;
     const uint32_t smem_lo = uniform_u32((smem_u32(smem) & 0x3FFFFu) >> 4);
     const uint32_t tmem_u = uniform_u32(tmem_base);
@@ -480,8 +478,6 @@ int run_stem7x7_wgrad(const void* x, const void* dy, float* dw, int64_t N, int64
   const int slab_b = slab > 7 * g.box_pairs * 16 ? slab : 7 * g.box_pairs * 16;
   g.stage_bytes = (g.dy_bytes + slab_b + 1023) / 1024 * 1024;
   g.Cin = (int)Cin;
-  const char* v = getenv("SIMCLR_STEM_WG_VARIANT");
-  g.variant = v ? atoi(v) : 0;
   CUtensorMap tx, tdy;
   int rc = make_tmap_pairs(&tx, x, (uint64_t)N, (uint64_t)H, (uint64_t)(W / 2), (uint32_t)g.box_pairs, 7);
   if (rc) return rc;

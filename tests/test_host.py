@@ -204,15 +204,13 @@ def test_profiles_are_consistent_with_their_sources(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out_txt, out_json = tmp_path / 'shares.txt', tmp_path / 'traffic.json'
     r = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'summarize_launches.py'),
-                        os.path.join(root, 'profiles', 'r01_launches_step.csv'), str(out_txt), str(out_json)],
+                        os.path.join(root, 'profiles', 'r02_launches_step.csv'), str(out_txt), str(out_json)],
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr[-2000:]
     new = json.load(open(out_json)); old = json.load(open(os.path.join(root, 'profiles', 'traffic.json')))
     assert new['launches'] == old['launches'] and abs(new['dram_bytes_per_launch'] - old['dram_bytes_per_launch']) < 1.0
-    assert open(out_txt).read() == open(os.path.join(root, 'profiles', 'r01_launch_shares.txt')).read()
-    latest = sorted(f for f in os.listdir(os.path.join(root, 'profiles')) if f.startswith('r01_bench_n1_v'))
-    latest.sort(key=lambda f: int(f.split('_v')[1].split('.')[0]))
-    line = json.load(open(os.path.join(root, 'profiles', latest[-1])))
+    assert open(out_txt).read() == open(os.path.join(root, 'profiles', 'r02_launch_shares.txt')).read()
+    line = json.load(open(os.path.join(root, 'profiles', 'r02_bench_n1_final.json')))
     roof = line['roofline']
     assert roof['traffic'] is not None and 0.9 < roof['traffic'] / roof['algorithmic_bytes'] < 1.1
     assert line['gpu_launches'] > 0 and line['e2e']['h2d_bytes_per_step'] > 0
