@@ -290,43 +290,53 @@ __device__ __forceinline__ void make_taps(float* wsm, int radius, float sigma) {
 // accumulators, the tap register file slides by one per input (the one-output-per-thread form was
 // bound by its 3 loads per FMA triple).
 
-// horizontal pass: features [B,H,W,3T] view t -> tmp [T*B,H,W,3]
-__global__ void blur_h_kernel(const float* __restrict__ f, float* __restrict__ tmp, int64_t B, int H, int W, int T,
-                              int radius, const float* __restrict__ sigma, const uint8_t* __restrict__ sel) {
+// horizontal pass: features [B,H,W,3T] view t -> tmp [T*B,H,W,3].  One CTA per image row: the row's 3W floats of view t
+// are staged in shared memory once (with `radius` zero pixels on both sides: the 'SAME' padding), then every thread
+// slides BLUR_OUT_H accumulators of one channel over it -- output (w, c) is sum_j k[j] * row[(w + j)*3 + c], so in the
+// flat row the window of a channel advances by 3 floats per tap.  The first version read the row straight from global
+// memory: 32 lanes, 12 pixels apart, 24-byte pixels -- a different sector per lane and load (0.70 ms, L1-bound).
+constexpr int BLUR_ROW_MAX = 4096;      // floats of one staged row: 3 * (W + 2*radius + BLUR_OUT_H)
+__global__ void __launch_bounds__(256)
+blur_h_kernel(const float* __restrict__ f, float* __restrict__ tmp, int64_t B, int H, int W, int T,
+              int radius, const float* __restrict__ sigma, const uint8_t* __restrict__ sel) {
   __shared__ float wsm[MAX_TAPS + 2 * TAP_PAD];
+  __shared__ float srow[BLUR_ROW_MAX];
   const int t = blockIdx.y;
   make_taps(wsm, radius, sigma[t]);
-  const int Wq = (W + BLUR_OUT_H - 1) / BLUR_OUT_H;
-  const int64_t total = B * H * Wq;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-    const int w0 = (int)(p % Wq) * BLUR_OUT_H;
-    const int64_t bh = p / Wq;          // b*H + h
+  const int64_t rows = B * H;
+  const int padded = 3 * (W + 2 * radius + BLUR_OUT_H);
+  const int groups = (W + BLUR_OUT_H - 1) / BLUR_OUT_H;       // per channel
+  for (int64_t bh = blockIdx.x; bh < rows; bh += gridDim.x) {
     const int64_t b = bh / H;
-    if (!sel[(int64_t)t * B + b]) continue;
-    float acc[BLUR_OUT_H][3];
-    float k[BLUR_OUT_H];
-#pragma unroll
-    for (int o = 0; o < BLUR_OUT_H; ++o) { acc[o][0] = acc[o][1] = acc[o][2] = 0.f; k[o] = 0.f; }
+    if (!sel[(int64_t)t * B + b]) continue;                   // uniform per CTA
     const float* row = f + bh * W * (int64_t)(3 * T) + 3 * t;
-#pragma unroll 4
-    for (int j = -radius; j <= radius + BLUR_OUT_H - 1; ++j) {
-      // output o sees this input through tap index (j - o) + radius
-#pragma unroll
-      for (int o = BLUR_OUT_H - 1; o > 0; --o) k[o] = k[o - 1];
-      k[0] = wsm[TAP_PAD + j + radius];
-      const int ww = w0 + j;
-      if (ww < 0 || ww >= W) continue;       // zero 'SAME' padding
-      const float* src = row + (int64_t)ww * (3 * T);
-      const float v0 = src[0], v1 = src[1], v2 = src[2];
-#pragma unroll
-      for (int o = 0; o < BLUR_OUT_H; ++o) {
-        acc[o][0] = fmaf(k[o], v0, acc[o][0]); acc[o][1] = fmaf(k[o], v1, acc[o][1]); acc[o][2] = fmaf(k[o], v2, acc[o][2]);
-      }
+    __syncthreads();                                          // the previous row's readers are done
+    for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+      const int w = i / 3 - radius, c = i - (i / 3) * 3;
+      srow[i] = (w >= 0 && w < W) ? row[(int64_t)w * (3 * T) + c] : 0.f;
     }
-    float* dst = tmp + (((int64_t)t * B * H + bh) * W + w0) * 3;
+    __syncthreads();
+    float* dst = tmp + ((int64_t)t * rows + bh) * W * 3;
+    for (int g = threadIdx.x; g < 3 * groups; g += blockDim.x) {
+      const int c = g % 3, w0 = (g / 3) * BLUR_OUT_H;
+      float acc[BLUR_OUT_H], k[BLUR_OUT_H];
 #pragma unroll
-    for (int o = 0; o < BLUR_OUT_H; ++o)
-      if (w0 + o < W) { dst[3 * o] = acc[o][0]; dst[3 * o + 1] = acc[o][1]; dst[3 * o + 2] = acc[o][2]; }
+      for (int o = 0; o < BLUR_OUT_H; ++o) { acc[o] = 0.f; k[o] = 0.f; }
+      const float* src = srow + w0 * 3 + c;                   // padded pixel w0 + j  <->  image pixel w0 + j - radius
+#pragma unroll 4
+      for (int j = 0; j <= 2 * radius + BLUR_OUT_H - 1; ++j) {
+        // output o sees input j through tap index j - o
+#pragma unroll
+        for (int o = BLUR_OUT_H - 1; o > 0; --o) k[o] = k[o - 1];
+        k[0] = wsm[TAP_PAD + j];
+        const float v = src[3 * j];
+#pragma unroll
+        for (int o = 0; o < BLUR_OUT_H; ++o) acc[o] = fmaf(k[o], v, acc[o]);
+      }
+#pragma unroll
+      for (int o = 0; o < BLUR_OUT_H; ++o)
+        if (w0 + o < W) dst[(w0 + o) * 3 + c] = acc[o];
+    }
   }
 }
 
@@ -558,7 +568,9 @@ int simclr_input_prep(const float* features, void* out, int dtype, int64_t B, in
   int64_t bx = (total + 255) / 256; const int64_t cap = (int64_t)num_sms() * 8; if (bx > cap) bx = cap;
   dim3 grid((unsigned)bx, (unsigned)T);
   if (use_blur) {
-    blur_h_kernel<<<grid, 256, 0, st>>>(features, tmp, B, (int)H, (int)W, (int)T, radius, sigma, selector);
+    SIMCLR_CHECK_ARG(3 * (W + 2 * radius + BLUR_OUT_H) <= BLUR_ROW_MAX, "input_prep: image too wide for the blur row buffer (W=%lld)", (long long)W);
+    int64_t rows_x = B * H; if (rows_x > (int64_t)num_sms() * 16) rows_x = (int64_t)num_sms() * 16;
+    blur_h_kernel<<<dim3((unsigned)rows_x, (unsigned)T), 256, 0, st>>>(features, tmp, B, (int)H, (int)W, (int)T, radius, sigma, selector);
     SIMCLR_CHECK_LAUNCH();
   }
   if (dtype == SIMCLR_F32) blur_v_kernel<float><<<grid, 256, 0, st>>>(features, tmp, (float*)out, B, (int)H, (int)W, (int)T, radius, sigma, selector, use_blur);
