@@ -328,12 +328,16 @@ def main(argv):
         raise app.UsageError('Too many command-line arguments.')
     rank = init_distributed()
     engine_lib.set_engine(engine_lib.Engine())
-    # --data_dir: an .npz of decoded images (data.ArrayBuilder.from_npz), else synthetic tensors
+    # --data_dir: a prepared TFDS directory (TFRecord shards, data.TFRecordBuilder), or an .npz of decoded images
+    # (data.ArrayBuilder.from_npz); without it: synthetic tensors of the input contract
     builder = None
     if FLAGS.data_dir:
         from . import data as data_lib
-        path = FLAGS.data_dir if os.path.isfile(FLAGS.data_dir) else os.path.join(FLAGS.data_dir, FLAGS.dataset + '.npz')
-        builder = data_lib.ArrayBuilder.from_npz(path)
+        npz = FLAGS.data_dir if os.path.isfile(FLAGS.data_dir) else os.path.join(FLAGS.data_dir, FLAGS.dataset + '.npz')
+        if os.path.isfile(npz):
+            builder = data_lib.ArrayBuilder.from_npz(npz)
+        else:
+            builder = data_lib.TFRecordBuilder(FLAGS.data_dir, FLAGS.dataset)
         builder.download_and_prepare()
         trainer = Trainer(num_classes=builder.info.features['label'].num_classes,
                           num_examples=builder.info.splits[FLAGS.train_split].num_examples)

@@ -310,3 +310,190 @@ def test_input_pipeline_host_logic(tmp_path):
             D.build_input_fn(b, 9, None, True)(ctx0, make_batch=fake)
     finally:
         flags_def.set_flags(**saved)
+
+
+def _example_message_classes():
+    """tf.train.Example / Features / Feature built with the protobuf runtime from the published schema
+    (tensorflow/core/example/{example,feature}.proto) -- an independent encoder / decoder for the wire format."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    fd = descriptor_pb2.FileDescriptorProto(name='simclr_test_example.proto', package='tftest', syntax='proto3')
+    F = descriptor_pb2.FieldDescriptorProto
+
+    def msg(name, fields):
+        m = fd.message_type.add(name=name)
+        for fname, num, typ, label, tname in fields:
+            f = m.field.add(name=fname, number=num, type=typ, label=label)
+            if tname:
+                f.type_name = tname
+        return m
+    msg('BytesList', [('value', 1, F.TYPE_BYTES, F.LABEL_REPEATED, None)])
+    msg('FloatList', [('value', 1, F.TYPE_FLOAT, F.LABEL_REPEATED, None)])
+    msg('Int64List', [('value', 1, F.TYPE_INT64, F.LABEL_REPEATED, None)])
+    feat = msg('Feature', [('bytes_list', 1, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, '.tftest.BytesList'),
+                           ('float_list', 2, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, '.tftest.FloatList'),
+                           ('int64_list', 3, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, '.tftest.Int64List')])
+    feat.oneof_decl.add(name='kind')
+    for f in feat.field:
+        f.oneof_index = 0
+    feats = msg('Features', [('feature', 1, F.TYPE_MESSAGE, F.LABEL_REPEATED, '.tftest.Features.FeatureEntry')])
+    entry = feats.nested_type.add(name='FeatureEntry')
+    entry.options.map_entry = True
+    entry.field.add(name='key', number=1, type=F.TYPE_STRING, label=F.LABEL_OPTIONAL)
+    entry.field.add(name='value', number=2, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL, type_name='.tftest.Feature')
+    msg('Example', [('features', 1, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, '.tftest.Features')])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    return message_factory.GetMessageClass(pool.FindMessageTypeByName('tftest.Example'))
+
+
+def test_tf_example_wire_format_against_protobuf():
+    """`tfrecord.parse_example` reads what the protobuf runtime serialises for the Example schema, and the protobuf
+    runtime parses what `tfrecord.encode_example` writes (negative labels, multi-element lists, empty features)."""
+    from simclr_b200 import tfrecord as T
+    Example = _example_message_classes()
+    ex = Example()
+    ex.features.feature['image'].bytes_list.value.append(b'\x00\xff\x10JPEGDATA' * 50)
+    ex.features.feature['label'].int64_list.value.extend([7])
+    ex.features.feature['neg'].int64_list.value.extend([-3, 1 << 40, 0])
+    ex.features.feature['scores'].float_list.value.extend([0.5, -2.25, 1e-3])
+    ex.features.feature['file_name'].bytes_list.value.extend([b'n01440764_10026.JPEG', b'second'])
+    ex.features.feature['empty'].bytes_list.SetInParent()
+    got = T.parse_example(ex.SerializeToString())
+    assert got['image'] == [b'\x00\xff\x10JPEGDATA' * 50] and got['label'] == [7] and got['neg'] == [-3, 1 << 40, 0]
+    assert got['file_name'] == [b'n01440764_10026.JPEG', b'second'] and got['empty'] == []
+    assert [round(x, 6) for x in got['scores']] == [0.5, -2.25, 0.001]
+    mine = T.encode_example({'image': b'abc' * 100, 'label': 999, 'neg': [-1, 5], 'scores': [1.5, 2.5]})
+    back = Example()
+    back.ParseFromString(mine)
+    assert back.features.feature['image'].bytes_list.value[0] == b'abc' * 100
+    assert list(back.features.feature['label'].int64_list.value) == [999]
+    assert list(back.features.feature['neg'].int64_list.value) == [-1, 5]
+    assert list(back.features.feature['scores'].float_list.value) == [1.5, 2.5]
+    assert T.parse_example(mine) == {'image': [b'abc' * 100], 'label': [999], 'neg': [-1, 5], 'scores': [1.5, 2.5]}
+
+
+def test_tfrecord_framing_and_tfds_directory(tmp_path):
+    """TFRecord framing (the CRC-32C check value and a corrupted header), and `data.TFRecordBuilder` over a directory in
+    the TFDS layout: split discovery, example counts from dataset_info.json, classes from features.json, PNG / JPEG
+    decode, whole files per input pipeline, shuffled repeat for training, one ordered pass for eval."""
+    import io, json
+    import numpy as np
+    from PIL import Image
+    from simclr_b200 import tfrecord as T, data as D, flags_def
+    p = str(tmp_path / 'x.tfrecord')
+    T.write_records(p, [b'', b'hello', b'x' * 1000])
+    assert list(T.read_records(p, verify_data_crc=True)) == [b'', b'hello', b'x' * 1000] and T.count_records(p) == 3
+    raw = bytearray(open(p, 'rb').read()); raw[2] ^= 1
+    open(p, 'wb').write(bytes(raw))
+    with pytest.raises(T.TFRecordError):
+        list(T.read_records(p))
+    # a TFDS-style directory: toy/1.0.0/toy-train.tfrecord-0000i-of-00004, toy-validation.tfrecord-00000-of-00001
+    d = tmp_path / 'tfds' / 'toy' / '1.0.0'
+    d.mkdir(parents=True)
+    rs = np.random.RandomState(0)
+    imgs = [rs.randint(0, 256, (20 + i % 5, 24 + i % 3, 3), dtype=np.uint8) for i in range(22)]
+    yy, xx = np.mgrid[0:20, 0:26]
+    imgs[20] = np.stack([4 * yy + 3 * xx, 200 - 5 * yy, 9 * xx], -1).astype(np.uint8)       # smooth: JPEG stays close
+    imgs[21] = imgs[20][::-1].copy()
+
+    def enc(a, fmt):
+        b = io.BytesIO(); Image.fromarray(a).save(b, format=fmt, **({'quality': 95} if fmt == 'JPEG' else {})); return b.getvalue()
+    shard_len = [5, 5, 5, 5]
+    k = 0
+    for s_i, n in enumerate(shard_len):
+        T.write_records(str(d / ('toy-train.tfrecord-%05d-of-00004' % s_i)),
+                        [T.encode_example({'image': enc(imgs[k + j], 'PNG'), 'label': (k + j) % 7, 'file_name': b'f%d' % (k + j)}) for j in range(n)])
+        k += n
+    T.write_records(str(d / 'toy-validation.tfrecord-00000-of-00001'),
+                    [T.encode_example({'image': enc(imgs[20 + j], 'JPEG'), 'label': j}) for j in range(2)])
+    json.dump({'name': 'toy', 'splits': [{'name': 'train', 'shardLengths': [str(x) for x in shard_len]}]}, open(d / 'dataset_info.json', 'w'))
+    json.dump({'featuresDict': {'features': {'label': {'classLabel': {'numClasses': '7'}}, 'image': {'image': {}}}}}, open(d / 'features.json', 'w'))
+    b = D.TFRecordBuilder(str(tmp_path / 'tfds'), 'toy')
+    assert b.info.splits['train'].num_examples == 20 and b.info.splits['validation'].num_examples == 2     # json / counted
+    assert b.info.features['label'].num_classes == 7
+    ctx = D.InputContext(2, 1, 2)
+    toks = list(b.tokens('train', ctx, False, None))
+    assert [l for _, l in toks] == [(i % 7) for i in list(range(5, 10)) + list(range(15, 20))]             # files 1 and 3
+    im, lab = b.fetch('train', toks[0])
+    assert lab == 5 and np.array_equal(im, imgs[5])                                                       # PNG: exact
+    jm, _ = b.fetch('validation', next(iter(b.tokens('validation', D.InputContext(1, 0, 1), False, None))))
+    assert jm.shape == imgs[20].shape and np.abs(jm.astype(int) - imgs[20].astype(int)).mean() < 3        # JPEG: lossy
+    # fewer files than pipelines: records are dealt round-robin
+    t3 = [list(b.tokens('validation', D.InputContext(3, q, 3), False, None)) for q in range(3)]
+    assert [len(x) for x in t3] == [1, 1, 0]
+    F = flags_def.FLAGS
+    if not F.is_parsed():
+        F(['test'])
+    saved = {k2: getattr(F, k2) for k2 in ('image_size', 'train_mode', 'train_split', 'eval_split')}
+    try:
+        flags_def.set_flags(image_size=64, train_mode='pretrain', train_split='train', eval_split='validation')
+        fake = lambda e, toks_: [l for _, l in toks_]
+        it = D.build_input_fn(b, 4, None, True)(D.InputContext(2, 0, 2), seed=5, make_batch=fake)
+        seen = sum([next(it) for _ in range(10)], [])
+        assert len(seen) == 20 and set(seen) <= {i % 7 for i in list(range(0, 5)) + list(range(10, 15))}  # pipeline 0: files 0, 2
+        ev = list(D.build_input_fn(b, 4, None, False)(D.InputContext(1, 0, 1), make_batch=fake))
+        assert ev == [[0, 1]]
+    finally:
+        flags_def.set_flags(**saved)
+
+
+def test_input_pipeline_batch_assembly_on_cpu(tmp_path, monkeypatch):
+    """The per-batch map of `build_input_fn` (fetch / decode -> augmentation draws -> kernel launches -> one-hot labels)
+    with the two GPU entry points replaced by CPU stand-ins: checks the host plumbing for both builders and all three
+    modes (two pretraining views, one finetune-training view, centre-crop eval)."""
+    import io
+    import numpy as np
+    import torch
+    from PIL import Image
+    from simclr_b200 import data as D, data_util as DU, tfrecord as T, flags_def
+    calls = []
+
+    def fake_train(images, draws, h, w, out=None, channel_offset=0):
+        assert len(images) == len(draws) and all(im.dtype == torch.uint8 and im.dim() == 3 for im in images)
+        calls.append(('train', len(images), channel_offset))
+        if out is None:
+            out = torch.zeros(len(images), h, w, 3)
+        out[..., channel_offset:channel_offset + 3] = torch.stack([im.float().mean() / 255.0 for im in images]).view(-1, 1, 1, 1)
+        return out
+
+    def fake_eval(images, h, w, crop=True):
+        calls.append(('eval', len(images), crop))
+        return torch.stack([im.float().mean() / 255.0 for im in images]).view(-1, 1, 1, 1).expand(len(images), h, w, 3).contiguous()
+    monkeypatch.setattr(DU, 'preprocess_for_train_batch', fake_train)
+    monkeypatch.setattr(DU, 'preprocess_for_eval_batch', fake_eval)
+    monkeypatch.setattr(D, 'get_engine', lambda: type('E', (), {'device': torch.device('cpu')})())
+    F = flags_def.FLAGS
+    if not F.is_parsed():
+        F(['test'])
+    saved = {k: getattr(F, k) for k in ('image_size', 'train_mode', 'train_split', 'eval_split', 'color_jitter_strength')}
+    rs = np.random.RandomState(1)
+    arr = rs.randint(0, 256, (12, 30, 34, 3), dtype=np.uint8)
+    labels = np.arange(12) % 4
+    d = tmp_path / 'toy' / '1.0.0'
+    d.mkdir(parents=True)
+
+    def png(a):
+        b = io.BytesIO(); Image.fromarray(a).save(b, format='PNG'); return b.getvalue()
+    T.write_records(str(d / 'toy-train.tfrecord-00000-of-00001'), [T.encode_example({'image': png(arr[i]), 'label': int(labels[i])}) for i in range(12)])
+    T.write_records(str(d / 'toy-validation.tfrecord-00000-of-00001'), [T.encode_example({'image': png(arr[i]), 'label': int(labels[i])}) for i in range(5)])
+    builders = [D.ArrayBuilder({'train': (arr, labels), 'validation': (arr[:5], labels[:5])}, 4),
+                D.TFRecordBuilder(str(tmp_path), 'toy', num_classes=4)]
+    try:
+        for b in builders:
+            flags_def.set_flags(image_size=48, train_mode='pretrain', train_split='train', eval_split='validation')
+            calls.clear()
+            f, lab = next(D.build_input_fn(b, 4, None, True)(D.InputContext(1, 0, 1), seed=2))
+            assert f.shape == (4, 48, 48, 6) and lab.shape == (4, 4) and torch.equal(lab.sum(1), torch.ones(4))
+            assert calls == [('train', 4, 0), ('train', 4, 3)] and torch.equal(f[..., 0], f[..., 3])      # both views of the same images
+            flags_def.set_flags(train_mode='finetune')
+            calls.clear()
+            f, lab = next(D.build_input_fn(b, 4, None, True)(D.InputContext(1, 0, 1), seed=2))
+            assert f.shape == (4, 48, 48, 3) and calls == [('train', 4, 0)]
+            calls.clear()
+            ev = list(D.build_input_fn(b, 4, None, False)(D.InputContext(1, 0, 1)))
+            assert [x[0].shape[0] for x in ev] == [4, 1] and calls == [('eval', 4, True), ('eval', 1, True)]
+            assert torch.equal(torch.cat([x[1] for x in ev]).argmax(1), torch.from_numpy(labels[:5]))
+            want = torch.from_numpy(arr[:5]).float().mean(dim=(1, 2, 3)) / 255.0                           # ordered pass, exact decode
+            assert torch.allclose(torch.cat([x[0][:, 0, 0, 0] for x in ev]), want)
+    finally:
+        flags_def.set_flags(**saved)
