@@ -4,9 +4,11 @@ slots, `global_step`), prunes to `keep_checkpoint_max`, and `try_restore_from_ch
 the reference's order: latest checkpoint in `model_dir` (weights + step + optimizer state), else
 `--checkpoint` (weights only, optional `--zero_init_logits_layer`).
 
-The container format is NumPy's (TensorFlow is not available to write or read tensor-bundle
-checkpoints); the variable NAMES are the reference's, so a converter from a released SimCLR
-checkpoint is a dictionary copy (HWIO kernels, [in, out] dense kernels: no transposes).
+Own checkpoints use NumPy's container format; the variable NAMES are the reference's.  TensorFlow checkpoints
+(`<prefix>.index` + `.data-*`: what the reference writes and what the released SimCLR weights are stored in) are READ
+through `tf_checkpoint.TensorBundleReader` -- `--checkpoint=<prefix>`, or a `model_dir` holding `ckpt-N.index` files:
+variables are joined on the object graph's `full_name` (HWIO kernels, [in, out] dense kernels: no transposes),
+optimizer slots are not imported.  That reader is unpinned against TensorFlow-written files (tf_checkpoint.py).
 """
 import glob
 import os
@@ -17,6 +19,7 @@ import torch
 from absl import logging
 
 from .flags_def import FLAGS
+from . import tf_checkpoint
 
 
 class CheckpointManager:
@@ -30,10 +33,46 @@ class CheckpointManager:
         ps = glob.glob(os.path.join(self.directory, 'ckpt-*.npz'))
         return sorted(ps, key=lambda p: int(re.search(r'ckpt-(\d+)\.npz$', p).group(1)))
 
+    def _tf_prefixes(self):
+        """`ckpt-N` prefixes of TensorFlow checkpoints in the directory (a model_dir written by the reference)."""
+        if not self.directory:
+            return []
+        ps = [p[:-6] for p in glob.glob(os.path.join(self.directory, 'ckpt-*.index'))]
+        return sorted((p for p in ps if re.search(r'ckpt-(\d+)$', p)), key=lambda p: int(re.search(r'ckpt-(\d+)$', p).group(1)))
+
     @property
     def latest_checkpoint(self):
         ps = self._paths()
-        return ps[-1] if ps else None
+        if ps:
+            return ps[-1]
+        tf = self._tf_prefixes()
+        return tf[-1] if tf else None
+
+    def _restore_tf(self, prefix, weights_only):
+        reader = tf_checkpoint.TensorBundleReader(prefix)
+        arrays = reader.variables_by_name()
+        byname = {v.name: v for v in self.model.variables}
+        hit = 0
+        for full, a in arrays.items():
+            v = byname.get(full + ':0') or byname.get(full)
+            if v is not None and tuple(a.shape) == tuple(v.shape):
+                v.value.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)))
+                hit += 1
+        logging.info('TensorFlow checkpoint %s: %d of %d model variables restored (%d tensors in the file)',
+                     prefix, hit, len(byname), len(arrays))
+        if hit == 0:
+            raise ValueError('no variable of %s matches the model (names are joined on the object graph full_name)' % prefix)
+        if weights_only:
+            return 0
+        step = 0
+        for key in ('global_step' + tf_checkpoint.VARIABLE_SUFFIX, 'global_step'):
+            if key in reader.entries:
+                step = int(reader.get_tensor(key))
+                break
+        if self.optimizer is not None:
+            logging.warning('optimizer slots of TensorFlow checkpoints are not imported: momentum restarts from zero')
+            self.optimizer.iterations = step
+        return step
 
     def save(self, step):
         os.makedirs(self.directory, exist_ok=True)
@@ -56,6 +95,8 @@ class CheckpointManager:
     def restore(self, path, weights_only=False):
         """Returns the restored global step (0 with `weights_only`).  Unknown / missing entries are skipped
         like `expect_partial()`."""
+        if tf_checkpoint.is_tf_checkpoint(path):
+            return self._restore_tf(path, weights_only)
         data = np.load(path)
         byname = {v.name: v for v in self.model.variables}
         for k in data.files:

@@ -497,3 +497,73 @@ def test_input_pipeline_batch_assembly_on_cpu(tmp_path, monkeypatch):
             assert torch.allclose(torch.cat([x[0][:, 0, 0, 0] for x in ev]), want)
     finally:
         flags_def.set_flags(**saved)
+
+
+def test_tensorflow_checkpoint_bundle_reader(tmp_path):
+    """tf_checkpoint: LevelDB-format table (prefix compression across restart points, several data blocks, block
+    checksums, footer magic), BundleEntryProto, the object graph's full_name join, bf16 / int64 tensors, and
+    CheckpointManager restoring from a TensorFlow-format prefix (`--checkpoint`) or from a model_dir of them."""
+    import struct
+    import numpy as np
+    import torch
+    from simclr_b200 import tf_checkpoint as TC, checkpoint as C
+    from simclr_b200.tfrecord import _varint, _ld
+    from simclr_b200.metrics import _masked_crc
+    rs = np.random.RandomState(0)
+    # many keys with long shared prefixes: exercises shared-prefix decoding, restart points and the index block
+    tensors, names = {}, {}
+    for i in range(150):
+        key = 'model/resnet_model/block_group%d/layer_with_a_long_name_%03d/kernel%s' % (i % 4, i, TC.VARIABLE_SUFFIX)
+        tensors[key] = rs.randn(1 + i % 3, 2, 3).astype(np.float32)
+        names[key] = 'resnet/block_group%d/conv2d_%d/kernel' % (i % 4, i)
+    tensors['global_step' + TC.VARIABLE_SUFFIX] = np.asarray(4321, dtype=np.int64)
+    tensors['flag'] = np.asarray([True, False])
+    prefix = str(tmp_path / 'tf' / 'ckpt-4321')
+    TC.write_bundle(prefix, tensors, names)
+    raw = open(prefix + '.index', 'rb').read()
+    assert struct.unpack('<Q', raw[-8:])[0] == 0xdb4775248b80fb57
+    r = TC.TensorBundleReader(prefix)
+    assert set(r.keys()) == set(tensors) | {TC.OBJECT_GRAPH_KEY} and r.keys() == sorted(r.keys(), key=lambda k: k.encode())
+    for k, v in tensors.items():
+        got = r.get_tensor(k)
+        assert got.dtype == v.dtype and got.shape == v.shape and np.array_equal(got, v)
+    assert int(r.get_tensor('global_step' + TC.VARIABLE_SUFFIX)) == 4321
+    byname = r.variables_by_name()
+    assert len(byname) == 150 and np.array_equal(byname['resnet/block_group3/conv2d_7/kernel'], tensors[[k for k in names if names[k].endswith('conv2d_7/kernel')][0]])
+    # the stored entry checksum is the masked CRC-32C of the tensor bytes
+    k0 = sorted(names)[0]
+    assert r.entries[k0].crc32c == _masked_crc(tensors[k0].tobytes())
+    # corruption inside a data block is detected
+    bad = bytearray(raw); bad[10] ^= 0xFF
+    open(prefix + '.index', 'wb').write(bytes(bad))
+    with pytest.raises(TC.CheckpointFormatError):
+        TC.TensorBundleReader(prefix)
+    open(prefix + '.index', 'wb').write(raw)
+    # a hand-assembled bf16 entry (DT_BFLOAT16 = 14): 1.0, -2.0 as 0x3F80, 0xC000
+    p2 = str(tmp_path / 'tf' / 'bf')
+    entry = _varint(1 << 3) + _varint(14) + _ld(2, _ld(2, _varint(1 << 3) + _varint(2))) + _varint(4 << 3) + _varint(0) + _varint(5 << 3) + _varint(4)
+    TC.write_table(p2 + '.index', [(b'', _varint(1 << 3) + _varint(1)), (b'w', entry)])
+    open(p2 + '.data-00000-of-00001', 'wb').write(struct.pack('<HH', 0x3F80, 0xC000))
+    assert TC.TensorBundleReader(p2).get_tensor('w').tolist() == [1.0, -2.0]
+
+    class V:
+        def __init__(self, name, t): self.name, self.value, self.shape = name, t, tuple(t.shape)
+
+    class FakeModel:
+        def __init__(self):
+            self.variables = [V('resnet/block_group3/conv2d_7/kernel:0', torch.zeros(2, 2, 3)), V('resnet/block_group0/conv2d_0/kernel:0', torch.zeros(1, 2, 3)),
+                              V('not/in/file:0', torch.ones(3)), V('resnet/block_group1/conv2d_1/kernel:0', torch.zeros(9, 9))]   # last: shape mismatch
+            self.trainable_variables = self.variables
+
+    class FakeOpt:
+        iterations = 0
+    m = FakeModel()
+    assert C.CheckpointManager(m, None, None).restore(prefix, weights_only=True) == 0
+    assert np.array_equal(m.variables[0].value.numpy(), byname['resnet/block_group3/conv2d_7/kernel'])
+    assert np.array_equal(m.variables[1].value.numpy(), byname['resnet/block_group0/conv2d_0/kernel'])
+    assert float(m.variables[2].value.sum()) == 3.0 and float(m.variables[3].value.abs().sum()) == 0.0
+    # a model_dir written by the reference: latest ckpt-N.index is picked up, the step comes from global_step
+    m2, o2 = FakeModel(), FakeOpt()
+    mgr = C.CheckpointManager(m2, o2, str(tmp_path / 'tf'))
+    assert mgr.latest_checkpoint == prefix
+    assert mgr.restore(mgr.latest_checkpoint) == 4321 and o2.iterations == 4321
