@@ -2,9 +2,10 @@
 the files `tf2/run.py:308-337` restores from (`tf.train.Checkpoint(model=..., global_step=..., optimizer=...)`) and the
 released SimCLR checkpoints are stored in.
 
-Format, restated from the TensorFlow sources (nothing is copied; TensorFlow is not installable here, so the reader is
-UNPINNED against files TensorFlow wrote -- it is exercised against the writer below and against the format's fixed
-points: footer magic, masked CRC-32C, block layout):
+Format, restated from the TensorFlow sources (nothing is copied).  TensorFlow is not installable here, so no file
+TensorFlow wrote has been read: what IS pinned against independent code (tests/test_host.py, using the protos TensorBoard
+vendors and its CRC-checking record reader) is the `TrackableObjectGraph` / `TensorShapeProto` field numbering, the dtype
+enum and the masked CRC-32C; the table layout and `BundleEntryProto` are exercised against the writer below only.
 
 * `<prefix>.index` is an immutable sorted string table in LevelDB's table format (tensorflow/core/lib/io/table*.cc,
   format.cc): data blocks of prefix-compressed entries `varint shared | varint unshared | varint value_len | key delta |

@@ -567,3 +567,64 @@ def test_tensorflow_checkpoint_bundle_reader(tmp_path):
     mgr = C.CheckpointManager(m2, o2, str(tmp_path / 'tf'))
     assert mgr.latest_checkpoint == prefix
     assert mgr.restore(mgr.latest_checkpoint) == 4321 and o2.iterations == 4321
+
+
+def test_formats_pinned_against_tensorboard_protos_and_reader(tmp_path):
+    """Independent implementations available offline (TensorBoard vendors TensorFlow's protos and ships a pure-Python
+    TFRecord reader that checks both CRCs): the object graph / shape / dtype numbering `tf_checkpoint` assumes, the
+    TFRecord framing `tfrecord.write_records` and `metrics.SummaryWriter` emit, and the scalar events they carry."""
+    tb = pytest.importorskip('tensorboard')
+    import numpy as np
+    from tensorboard.compat.proto import trackable_object_graph_pb2 as TG, types_pb2, tensor_shape_pb2, event_pb2
+    from tensorboard.compat.tensorflow_stub.pywrap_tensorflow import PyRecordReader_New
+    from simclr_b200 import tf_checkpoint as TC, tfrecord as T, metrics as M
+    # dtype numbering
+    for code, dt in TC._DTYPES.items():
+        name = {'bfloat16': 'DT_BFLOAT16'}.get(dt) if isinstance(dt, str) else None
+        name = name or {'float32': 'DT_FLOAT', 'float64': 'DT_DOUBLE', 'int32': 'DT_INT32', 'uint8': 'DT_UINT8', 'int16': 'DT_INT16',
+                        'int8': 'DT_INT8', 'int64': 'DT_INT64', 'bool': 'DT_BOOL', 'uint16': 'DT_UINT16', 'float16': 'DT_HALF',
+                        'uint32': 'DT_UINT32', 'uint64': 'DT_UINT64'}[np.dtype(dt).name]
+        assert getattr(types_pb2, name) == code, name
+    assert types_pb2.DT_STRING == TC.DT_STRING
+    # an object graph serialised by the real proto classes, stored as the bundle's string tensor, read back by our parser
+    g = TG.TrackableObjectGraph()
+    root = g.nodes.add()
+    for i, (key, full) in enumerate([('model/a/kernel' + TC.VARIABLE_SUFFIX, 'resnet/conv2d/kernel'), ('model/a/bias' + TC.VARIABLE_SUFFIX, 'head/bias')]):
+        c = root.children.add(); c.node_id = i + 1; c.local_name = 'child%d' % i
+        n = g.nodes.add()
+        a = n.attributes.add(); a.name = 'VARIABLE_VALUE'; a.full_name = full; a.checkpoint_key = key
+        n.slot_variables.add().slot_name = 'Momentum'
+    prefix = str(tmp_path / 'ck')
+    tensors = {'model/a/kernel' + TC.VARIABLE_SUFFIX: np.arange(6, dtype=np.float32).reshape(1, 1, 2, 3),
+               'model/a/bias' + TC.VARIABLE_SUFFIX: np.ones(3, dtype=np.float32), TC.OBJECT_GRAPH_KEY: g.SerializeToString()}
+    TC.write_bundle(prefix, tensors)
+    r = TC.TensorBundleReader(prefix)
+    assert sorted(r.object_graph()) == sorted([(a.checkpoint_key, a.full_name, a.name) for n in g.nodes for a in n.attributes])
+    assert set(r.variables_by_name()) == {'resnet/conv2d/kernel', 'head/bias'}
+    # ... and our writer's object graph parses with the real proto classes
+    TC.write_bundle(prefix + '2', {k: v for k, v in tensors.items() if k != TC.OBJECT_GRAPH_KEY}, {k: 'n/' + k[:9] for k in tensors if k != TC.OBJECT_GRAPH_KEY})
+    g2 = TG.TrackableObjectGraph(); g2.ParseFromString(TC.TensorBundleReader(prefix + '2').get_string(TC.OBJECT_GRAPH_KEY))
+    assert len(g2.nodes) == 3 and len(g2.nodes[0].children) == 2 and g2.nodes[1].attributes[0].name == 'VARIABLE_VALUE'
+    # TensorShapeProto as written into BundleEntryProto.shape
+    sh = tensor_shape_pb2.TensorShapeProto(); sh.ParseFromString(TC._shape_proto((7, 1, 3)))
+    assert [d.size for d in sh.dim] == [7, 1, 3]
+    assert TC._parse_shape(memoryview(tensor_shape_pb2.TensorShapeProto(dim=[tensor_shape_pb2.TensorShapeProto.Dim(size=5), tensor_shape_pb2.TensorShapeProto.Dim(size=0)]).SerializeToString())) == (5, 0)
+    # TFRecord framing: TensorBoard's reader (verifies length and data CRCs) reads what we write
+    p = str(tmp_path / 'r.tfrecord')
+    payloads = [b'', b'abc', bytes(range(256)) * 9]
+    T.write_records(p, payloads)
+    rd = PyRecordReader_New(p); got = []
+    while True:
+        try:
+            rd.GetNext()
+        except Exception:
+            break
+        got.append(rd.record())
+    assert got == payloads
+    # event file written by metrics.SummaryWriter -> real Event protos
+    w = M.SummaryWriter(str(tmp_path)); w.scalar('train/total_loss', 1.5, step=7); w.scalar('lr', 0.25, step=8); w.flush(); w.close()
+    evs = []
+    for rec in T.read_records(w.path, verify_data_crc=True):
+        e = event_pb2.Event(); e.ParseFromString(rec); evs.append(e)
+    vals = [(e.step, v.tag, v.simple_value) for e in evs for v in e.summary.value]
+    assert vals == [(7, 'train/total_loss', 1.5), (8, 'lr', 0.25)] and evs[0].file_version.startswith('brain.Event')
