@@ -319,3 +319,24 @@ def write_bundle(prefix, tensors, names=None):
     write_table(prefix + '.index', [(b'', header)] + items)
     with open(prefix + '.data-00000-of-00001', 'wb') as fh:
         fh.write(bytes(blob))
+
+
+def main(argv=None):
+    """`python -m simclr_b200.tf_checkpoint <prefix>`: list the tensors of a TensorFlow checkpoint (key, dtype, shape)
+    and the variable name each object-graph key maps to."""
+    import sys
+    args = list(sys.argv[1:] if argv is None else argv)
+    if len(args) != 1:
+        print('usage: python -m simclr_b200.tf_checkpoint <checkpoint prefix>')
+        return 2
+    r = TensorBundleReader(args[0])
+    names = {k: full for k, full, attr in r.object_graph() if attr == 'VARIABLE_VALUE'}
+    for k, e in r.entries.items():
+        dt = 'string' if e.dtype == DT_STRING else str(_DTYPES.get(e.dtype, 'dtype %d' % e.dtype))
+        print('%-90s %-9s %-20s %s' % (k, dt, list(e.shape), names.get(k, '')))
+    print('%d tensors, %d shard(s)' % (len(r.entries), r.num_shards))
+    return 0
+
+
+if __name__ == '__main__':
+    raise SystemExit(main())
